@@ -1,0 +1,348 @@
+// FP64 GEMM / TRRK on the DMMA tensor pipe (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4,
+// the only f64 MMA shape sm_100a has; tcgen05 has no f64 kind).
+//
+// Replaces blas::Gemm<double> (reference include/El/core/imports/blas.hpp:570-603 ->
+// dgemm_, src/core/imports/blas/Gemm.hpp:431) and, with MODE != 0, the whole
+// LocalTrrk recursion (src/blas_like/level3/Trrk/Local.hpp:782-830) as ONE masked
+// GEMM: tiles entirely outside the global triangle exit before loading anything,
+// tiles that straddle it mask per element in the epilogue.
+//
+// Layout: column-major operands.  op(A) is m x k, op(B) is k x n.  Each operand
+// tile is staged in shared memory in one of two layouts, chosen by which
+// dimension is contiguous in global memory:
+//   MN-major  s[k][LDMN]   (A 'N', B 'T')   pitch 132 doubles
+//   K-major   s[r][LDK]    (A 'T', B 'N')   pitch 20 doubles
+// Both pitches are == 4 (mod 16) doubles, which makes every half-warp LDS.64 of
+// an m8n8k4 fragment (lane -> row g=lane/4, k t=lane%4) hit 16 distinct bank
+// pairs: conflict-free without swizzling.
+//
+// CTA tile 128x128x16, 8 warps (2 along M x 4 along N, warp tile 64x32),
+// 4-stage cp.async pipeline (160 KB smem, one CTA per SM), accumulators in
+// registers (64 doubles / thread).
+#include "../common.hpp"
+#include "elb200_blas.h"
+
+namespace elb200 {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int STAGES = 4;
+constexpr int NTHREADS = 256;
+constexpr int LDMN = BM + 4;  // 132
+constexpr int LDK = BK + 4;   // 20
+constexpr int TILE_DOUBLES = (BM * LDK > BK * LDMN) ? BM * LDK : BK * LDMN;  // 2560
+constexpr int STAGE_DOUBLES = 2 * TILE_DOUBLES;
+constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;  // 163840
+constexpr int GROUP_N = 8;  // tile columns per rasterisation group
+
+struct GemmArgs {
+    i64 m, n, k;
+    const double* A;
+    i64 lda;
+    const double* B;
+    i64 ldb;
+    double* C;
+    i64 ldc;
+    double alpha, beta;
+    // global index of local (i,j) is (gi0 + i*gis, gj0 + j*gjs) -- TRRK only
+    i64 gi0, gis, gj0, gjs;
+    int vecA, vecB;  // 1 when 16-byte cp.async is legal for that operand
+    i64 tilesM, tilesN;
+};
+
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src),
+                 "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(unsigned dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(src),
+                 "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// Stage one 128 x 16 operand tile.  X(r,kk) is the logical op(X) entry; R, K are
+// the logical extents; rows beyond them are zero-filled (cp.async src-size 0).
+template <bool KMAJOR>
+__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ X, i64 ld, i64 R,
+                                          i64 K, i64 r0, i64 k0, int vec, int tid) {
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(s);
+    if (!KMAJOR) {
+        // X(r,kk) at X[r + kk*ld]; smem s[kk*LDMN + r]
+        if (vec) {
+#pragma unroll
+            for (int it = 0; it < (BK * BM / 2) / NTHREADS; ++it) {
+                int id = tid + it * NTHREADS;
+                int kk = id / (BM / 2);
+                int rr = (id % (BM / 2)) * 2;
+                i64 r = r0 + rr, kg = k0 + kk;
+                int valid = 0;
+                if (kg < K) {
+                    i64 rem = R - r;
+                    valid = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+                }
+                const double* src = valid ? (X + r + kg * ld) : X;
+                cp_async16(sbase + (unsigned)(kk * LDMN + rr) * 8u, src, valid);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < (BK * BM) / NTHREADS; ++it) {
+                int id = tid + it * NTHREADS;
+                int kk = id / BM;
+                int rr = id % BM;
+                i64 r = r0 + rr, kg = k0 + kk;
+                int valid = (kg < K && r < R) ? 8 : 0;
+                const double* src = valid ? (X + r + kg * ld) : X;
+                cp_async8(sbase + (unsigned)(kk * LDMN + rr) * 8u, src, valid);
+            }
+        }
+    } else {
+        // X(r,kk) at X[kk + r*ld]; smem s[r*LDK + kk]
+        if (vec) {
+#pragma unroll
+            for (int it = 0; it < (BM * BK / 2) / NTHREADS; ++it) {
+                int id = tid + it * NTHREADS;
+                int rr = id / (BK / 2);
+                int kk = (id % (BK / 2)) * 2;
+                i64 r = r0 + rr, kg = k0 + kk;
+                int valid = 0;
+                if (r < R) {
+                    i64 rem = K - kg;
+                    valid = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+                }
+                const double* src = valid ? (X + kg + r * ld) : X;
+                cp_async16(sbase + (unsigned)(rr * LDK + kk) * 8u, src, valid);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < (BM * BK) / NTHREADS; ++it) {
+                int id = tid + it * NTHREADS;
+                int rr = id / BK;
+                int kk = id % BK;
+                i64 r = r0 + rr, kg = k0 + kk;
+                int valid = (kg < K && r < R) ? 8 : 0;
+                const double* src = valid ? (X + kg + r * ld) : X;
+                cp_async8(sbase + (unsigned)(rr * LDK + kk) * 8u, src, valid);
+            }
+        }
+    }
+}
+
+template <bool KMAJOR>
+__device__ __forceinline__ double frag(const double* s, int r, int kk) {
+    return KMAJOR ? s[r * LDK + kk] : s[kk * LDMN + r];
+}
+
+// MODE 0: full GEMM; 1: lower-triangle TRRK; 2: upper-triangle TRRK
+template <bool A_KMAJOR, bool B_KMAJOR, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(const GemmArgs p) {
+    extern __shared__ __align__(128) double smem[];
+
+    // ---- tile coordinates (grouped rasterisation for L2 reuse) ----
+    const i64 tile = blockIdx.x;
+    const i64 group_sz = (i64)GROUP_N * p.tilesM;
+    const i64 gid = tile / group_sz;
+    const i64 first_n = gid * GROUP_N;
+    const i64 gw = (p.tilesN - first_n < GROUP_N) ? (p.tilesN - first_n) : GROUP_N;
+    const i64 in_group = tile % group_sz;
+    const i64 tm = in_group / gw;
+    const i64 tn = first_n + in_group % gw;
+    const i64 m0 = tm * BM, n0 = tn * BN;
+
+    if (MODE != 0) {
+        const i64 mlast = (m0 + BM - 1 < p.m - 1) ? (m0 + BM - 1) : (p.m - 1);
+        const i64 nlast = (n0 + BN - 1 < p.n - 1) ? (n0 + BN - 1) : (p.n - 1);
+        if (MODE == 1) {  // lower: need some gi >= gj
+            if (p.gi0 + mlast * p.gis < p.gj0 + n0 * p.gjs) return;
+        } else {  // upper: need some gi <= gj
+            if (p.gi0 + m0 * p.gis > p.gj0 + nlast * p.gjs) return;
+        }
+    }
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp & 1) * 64, wn0 = (warp >> 1) * 32;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const i64 KT = (p.k + BK - 1) / BK;
+
+    // ---- prologue: STAGES-1 tiles in flight ----
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT) {
+            double* sa = smem + s * STAGE_DOUBLES;
+            load_tile<A_KMAJOR>(sa, p.A, p.lda, p.m, p.k, m0, (i64)s * BK, p.vecA, tid);
+            load_tile<B_KMAJOR>(sa + TILE_DOUBLES, p.B, p.ldb, p.n, p.k, n0, (i64)s * BK, p.vecB,
+                                tid);
+        }
+        cp_async_commit();
+    }
+
+    for (i64 kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            const i64 nk = kt + STAGES - 1;
+            if (nk < KT) {
+                double* sa = smem + (nk % STAGES) * STAGE_DOUBLES;
+                load_tile<A_KMAJOR>(sa, p.A, p.lda, p.m, p.k, m0, nk * BK, p.vecA, tid);
+                load_tile<B_KMAJOR>(sa + TILE_DOUBLES, p.B, p.ldb, p.n, p.k, n0, nk * BK, p.vecB,
+                                    tid);
+            }
+            cp_async_commit();
+        }
+        const double* sa = smem + (kt % STAGES) * STAGE_DOUBLES;
+        const double* sb = sa + TILE_DOUBLES;
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ++ks) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = frag<A_KMAJOR>(sa, wm0 + i * 8 + g, ks * 4 + t);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = frag<B_KMAJOR>(sb, wn0 + j * 8 + g, ks * 4 + t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- epilogue: C = alpha*acc + beta*C (masked for TRRK) ----
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const i64 col = n0 + wn0 + j * 8 + 2 * t + e;
+            if (col >= p.n) continue;
+            const i64 gj = p.gj0 + col * p.gjs;
+            double* cptr = p.C + col * p.ldc;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const i64 row = m0 + wm0 + i * 8 + g;
+                if (row >= p.m) continue;
+                if (MODE == 1 && (p.gi0 + row * p.gis < gj)) continue;
+                if (MODE == 2 && (p.gi0 + row * p.gis > gj)) continue;
+                double v = alpha * acc[i][j][e];
+                if (beta != 0.0) v += beta * cptr[row];
+                cptr[row] = v;
+            }
+        }
+    }
+}
+
+template <bool AK, bool BK_, int MODE>
+void launch(const GemmArgs& a, cudaStream_t s) {
+    static bool configured = false;
+    auto kern = gemm_f64_kernel<AK, BK_, MODE>;
+    if (!configured) {
+        ELB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SMEM_BYTES));
+        configured = true;
+    }
+    const i64 tiles = a.tilesM * a.tilesN;
+    kern<<<(unsigned)tiles, NTHREADS, SMEM_BYTES, s>>>(a);
+    ELB_LAUNCH_CHECK();
+}
+
+template <int MODE>
+void dispatch(bool ak, bool bk, const GemmArgs& a, cudaStream_t s) {
+    if (ak) {
+        if (bk) launch<true, true, MODE>(a, s);
+        else launch<true, false, MODE>(a, s);
+    } else {
+        if (bk) launch<false, true, MODE>(a, s);
+        else launch<false, false, MODE>(a, s);
+    }
+}
+
+bool is_trans(char c, const char* what) {
+    c = up(c);
+    if (c == 'N') return false;
+    if (c == 'T' || c == 'C') return true;
+    throw std::logic_error(std::string("invalid orientation for ") + what);
+}
+
+}  // namespace
+
+// mode 0 = gemm, 1 = lower trrk, 2 = upper trrk
+void dgemm_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, double alpha,
+                  const double* A, i64 lda, const double* B, i64 ldb, double beta, double* C,
+                  i64 ldc, i64 gi0, i64 gis, i64 gj0, i64 gjs, cudaStream_t s) {
+    if (m < 0 || n < 0 || k < 0) throw std::logic_error("dgemm: negative dimension");
+    const bool ta = is_trans(transA, "A"), tb = is_trans(transB, "B");
+    if (m == 0 || n == 0) return;
+    if (lda < ((ta ? k : m) > 1 ? (ta ? k : m) : 1)) throw std::logic_error("dgemm: lda too small");
+    if (ldb < ((tb ? n : k) > 1 ? (tb ? n : k) : 1)) throw std::logic_error("dgemm: ldb too small");
+    if (ldc < (m > 1 ? m : 1)) throw std::logic_error("dgemm: ldc too small");
+    GemmArgs a;
+    a.m = m; a.n = n; a.k = (alpha == 0.0) ? 0 : k;
+    a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc;
+    a.alpha = alpha; a.beta = beta;
+    a.gi0 = gi0; a.gis = gis; a.gj0 = gj0; a.gjs = gjs;
+    a.vecA = (((uintptr_t)A & 15) == 0 && (lda % 2) == 0) ? 1 : 0;
+    a.vecB = (((uintptr_t)B & 15) == 0 && (ldb % 2) == 0) ? 1 : 0;
+    a.tilesM = ceil_div(m, BM);
+    a.tilesN = ceil_div(n, BN);
+    // A 'T' is K-major; B 'N' is K-major
+    const bool ak = ta, bk = !tb;
+    if (mode == 0) dispatch<0>(ak, bk, a, s);
+    else if (mode == 1) dispatch<1>(ak, bk, a, s);
+    else dispatch<2>(ak, bk, a, s);
+}
+
+}  // namespace elb200
+
+extern "C" {
+
+int elb200_dgemm(char transA, char transB, int64_t m, int64_t n, int64_t k, double alpha,
+                 const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
+                 double* C, int64_t ldc, elb200_stream_t s) {
+    return elb200::guarded([&] {
+        elb200::dgemm_device(0, transA, transB, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, 1,
+                             0, 1, (cudaStream_t)s);
+    });
+}
+
+int elb200_dtrrk(char uplo, char transA, char transB, int64_t m, int64_t n, int64_t k,
+                 double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
+                 double beta, double* C, int64_t ldc, int64_t rowShift, int64_t rowStride,
+                 int64_t colShift, int64_t colStride, elb200_stream_t s) {
+    return elb200::guarded([&] {
+        const char u = elb200::up(uplo);
+        if (u != 'L' && u != 'U') throw std::logic_error("dtrrk: uplo must be 'L' or 'U'");
+        elb200::dgemm_device(u == 'L' ? 1 : 2, transA, transB, m, n, k, alpha, A, lda, B, ldb,
+                             beta, C, ldc, rowShift, rowStride, colShift, colStride,
+                             (cudaStream_t)s);
+    });
+}
+
+int elb200_dsyrk(char uplo, char trans, int64_t n, int64_t k, double alpha, const double* A,
+                 int64_t lda, double beta, double* C, int64_t ldc, elb200_stream_t s) {
+    return elb200::guarded([&] {
+        const char u = elb200::up(uplo);
+        if (u != 'L' && u != 'U') throw std::logic_error("dsyrk: uplo must be 'L' or 'U'");
+        const bool tr = elb200::up(trans) != 'N';
+        // 'N': C = A A^T ; 'T': C = A^T A
+        elb200::dgemm_device(u == 'L' ? 1 : 2, tr ? 'T' : 'N', tr ? 'N' : 'T', n, n, k, alpha, A,
+                             lda, A, lda, beta, C, ldc, 0, 1, 0, 1, (cudaStream_t)s);
+    });
+}
+
+}  // extern "C"

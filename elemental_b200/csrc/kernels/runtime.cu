@@ -1,0 +1,99 @@
+// Layer runtime: last-error text, current stream, device check and the FP64
+// tensor-pipe (DMMA) ceiling probe that bench.py uses as roofline denominator.
+#include "../common.hpp"
+#include "elb200_blas.h"
+
+namespace elb200 {
+
+static thread_local std::string g_last_error;
+static thread_local cudaStream_t g_stream = nullptr;
+
+void set_last_error(const std::string& s) { g_last_error = s; }
+const char* last_error() { return g_last_error.c_str(); }
+cudaStream_t current_stream() { return g_stream; }
+void set_current_stream(cudaStream_t s) { g_stream = s; }
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        ELB_CUDA(cudaGetDevice(&dev));
+        ELB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    }
+    return n;
+}
+
+namespace {
+// 8 warps per CTA, each with 16 independent m8n8k4 accumulator tiles.
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink) {
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            asm volatile(
+                "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                : "+d"(c[i][0]), "+d"(c[i][1])
+                : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) sink[0] = s;  // keep the loop alive
+}
+}  // namespace
+}  // namespace elb200
+
+extern "C" {
+
+const char* elb200_last_error(void) { return elb200::last_error(); }
+int elb200_version(void) { return 100; }
+
+int elb200_device_check(void) {
+    return elb200::guarded([] {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0)
+            throw std::runtime_error(
+                "elb200: no CUDA device visible -- this layer has no CPU fallback");
+        int dev = 0, major = 0;
+        ELB_CUDA(cudaGetDevice(&dev));
+        ELB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+        if (major != 10)
+            throw std::runtime_error("elb200: kernels are built for sm_100a only");
+    });
+}
+
+void elb200_set_stream(elb200_stream_t s) { elb200::set_current_stream((cudaStream_t)s); }
+elb200_stream_t elb200_get_stream(void) { return (elb200_stream_t)elb200::current_stream(); }
+
+int elb200_dmma_peak(int iters, double* flops_per_s, float* ms_out) {
+    return elb200::guarded([&] {
+        using namespace elb200;
+        const int ctas = sm_count() * 2;
+        double* sink = nullptr;
+        ELB_CUDA(cudaMalloc(&sink, 8));
+        cudaEvent_t e0, e1;
+        ELB_CUDA(cudaEventCreate(&e0));
+        ELB_CUDA(cudaEventCreate(&e1));
+        dmma_peak_kernel<<<ctas, 256>>>(iters / 10 + 1, sink);  // warm-up
+        ELB_CUDA(cudaEventRecord(e0));
+        dmma_peak_kernel<<<ctas, 256>>>(iters, sink);
+        ELB_CUDA(cudaEventRecord(e1));
+        ELB_CUDA(cudaEventSynchronize(e1));
+        ELB_LAUNCH_CHECK();
+        float ms = 0.f;
+        ELB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        // per warp per iteration: 16 MMAs x (8*8*4) FMAs x 2 flops
+        const double flops = double(ctas) * 8.0 * double(iters) * 16.0 * 512.0;
+        if (flops_per_s) *flops_per_s = flops / (ms * 1e-3);
+        if (ms_out) *ms_out = ms;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaFree(sink);
+    });
+}
+
+}  // extern "C"

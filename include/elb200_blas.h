@@ -1,0 +1,202 @@
+/*
+ * elb200_blas.h -- the leaf C-ABI of the B200-native Elemental hot path.
+ *
+ * Every entry point takes DEVICE pointers (column-major, leading dimension in
+ * elements) and launches hand-written sm_100a kernels on the given CUDA
+ * stream.  There is no CPU fallback: without a CUDA device every call fails
+ * with a nonzero return code and a message in elb200_last_error().
+ *
+ * What each group replaces in the reference (paths relative to the Elemental
+ * tree):
+ *
+ *   elb200_{s,d,c,z}gemm   <- El::blas::Gemm   include/El/core/imports/blas.hpp:570-603,
+ *                             which binds sgemm_/dgemm_/cgemm_/zgemm_
+ *                             (src/core/imports/blas/Gemm.hpp:13-40,388,431,471,511)
+ *   elb200_{s,d,c,z}trsm   <- El::blas::Trsm   blas.hpp:884-913 (src/core/imports/blas/Trsm.hpp:12-33)
+ *   elb200_{s,d}syrk, elb200_{c,z}herk, elb200_{c,z}syrk
+ *                          <- El::blas::Syrk/Herk  blas.hpp:689-722,813-846
+ *   elb200_{s,d,c,z}trrk   <- the LocalTrrk recursion, src/blas_like/level3/Trrk/Local.hpp:782-830
+ *                             (one masked GEMM instead of gemm + AxpyTrapezoid leaves)
+ *   elb200_{s,d,c,z}potrf  <- cholesky::LowerVariant3Unblocked / UpperVariant3Unblocked,
+ *                             src/lapack_like/factor/Cholesky/LowerVariant3.hpp:16-41,
+ *                             UpperVariant3.hpp:16-46 (the reference never calls LAPACK potrf)
+ *   Fortran-ABI symbols (dgemm_, dtrsm_, dsyrk_, zherk_, ...) with the exact
+ *   prototypes the reference declares; they forward to the functions above on
+ *   the layer's current stream (elb200_set_stream).
+ */
+#ifndef ELB200_BLAS_H
+#define ELB200_BLAS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* elb200_stream_t; /* == cudaStream_t */
+typedef struct { float re, im; } elb200_c32;
+typedef struct { double re, im; } elb200_c64;
+
+/* ---- runtime ---------------------------------------------------------- */
+const char* elb200_last_error(void);
+int elb200_version(void);
+/* 0 when a usable sm_100 device is present, nonzero (+last_error) otherwise */
+int elb200_device_check(void);
+void elb200_set_stream(elb200_stream_t s);
+elb200_stream_t elb200_get_stream(void);
+
+/* ---- GEMM: C := alpha op(A) op(B) + beta C ---------------------------- */
+/* trans in {'N','T','C'}; for real types 'C' == 'T' (blas/Gemm.hpp:386-387) */
+int elb200_dgemm(char transA, char transB, int64_t m, int64_t n, int64_t k,
+                 double alpha, const double* A, int64_t lda,
+                 const double* B, int64_t ldb,
+                 double beta, double* C, int64_t ldc, elb200_stream_t s);
+int elb200_sgemm(char transA, char transB, int64_t m, int64_t n, int64_t k,
+                 float alpha, const float* A, int64_t lda,
+                 const float* B, int64_t ldb,
+                 float beta, float* C, int64_t ldc, elb200_stream_t s);
+int elb200_zgemm(char transA, char transB, int64_t m, int64_t n, int64_t k,
+                 elb200_c64 alpha, const elb200_c64* A, int64_t lda,
+                 const elb200_c64* B, int64_t ldb,
+                 elb200_c64 beta, elb200_c64* C, int64_t ldc, elb200_stream_t s);
+int elb200_cgemm(char transA, char transB, int64_t m, int64_t n, int64_t k,
+                 elb200_c32 alpha, const elb200_c32* A, int64_t lda,
+                 const elb200_c32* B, int64_t ldb,
+                 elb200_c32 beta, elb200_c32* C, int64_t ldc, elb200_stream_t s);
+/* float GEMM on tcgen05 (kind::tf32) with the 3xTF32 operand split;
+ * relative error per product ~2^-21 instead of 2^-24 */
+int elb200_sgemm_3xtf32(char transA, char transB, int64_t m, int64_t n, int64_t k,
+                 float alpha, const float* A, int64_t lda,
+                 const float* B, int64_t ldb,
+                 float beta, float* C, int64_t ldc, elb200_stream_t s);
+
+/* ---- TRRK: triangle-restricted rank-k update --------------------------- */
+/* C_tri := alpha op(A) op(B) + beta C_tri, touching only entries whose GLOBAL
+ * indices (gi = rowShift + i*rowStride, gj = colShift + j*colStride) lie in
+ * the uplo triangle (gi >= gj for 'L', gi <= gj for 'U').  With shift 0 and
+ * stride 1 this is a plain local Trrk; with the [MC,MR] shifts/strides it is
+ * the staircase update of LocalTrrk (Trrk/Local.hpp:782-830). */
+int elb200_dtrrk(char uplo, char transA, char transB, int64_t m, int64_t n, int64_t k,
+                 double alpha, const double* A, int64_t lda,
+                 const double* B, int64_t ldb,
+                 double beta, double* C, int64_t ldc,
+                 int64_t rowShift, int64_t rowStride,
+                 int64_t colShift, int64_t colStride, elb200_stream_t s);
+int elb200_strrk(char uplo, char transA, char transB, int64_t m, int64_t n, int64_t k,
+                 float alpha, const float* A, int64_t lda,
+                 const float* B, int64_t ldb,
+                 float beta, float* C, int64_t ldc,
+                 int64_t rowShift, int64_t rowStride,
+                 int64_t colShift, int64_t colStride, elb200_stream_t s);
+int elb200_ztrrk(char uplo, char transA, char transB, int64_t m, int64_t n, int64_t k,
+                 elb200_c64 alpha, const elb200_c64* A, int64_t lda,
+                 const elb200_c64* B, int64_t ldb,
+                 elb200_c64 beta, elb200_c64* C, int64_t ldc,
+                 int64_t rowShift, int64_t rowStride,
+                 int64_t colShift, int64_t colStride, elb200_stream_t s);
+int elb200_ctrrk(char uplo, char transA, char transB, int64_t m, int64_t n, int64_t k,
+                 elb200_c32 alpha, const elb200_c32* A, int64_t lda,
+                 const elb200_c32* B, int64_t ldb,
+                 elb200_c32 beta, elb200_c32* C, int64_t ldc,
+                 int64_t rowShift, int64_t rowStride,
+                 int64_t colShift, int64_t colStride, elb200_stream_t s);
+
+/* ---- SYRK / HERK (local, blas.hpp:689-722,813-846) --------------------- */
+/* trans 'N': C := alpha A A^T + beta C (A is n x k); 'T'/'C': A^T A (A is k x n) */
+int elb200_dsyrk(char uplo, char trans, int64_t n, int64_t k, double alpha,
+                 const double* A, int64_t lda, double beta, double* C, int64_t ldc,
+                 elb200_stream_t s);
+int elb200_ssyrk(char uplo, char trans, int64_t n, int64_t k, float alpha,
+                 const float* A, int64_t lda, float beta, float* C, int64_t ldc,
+                 elb200_stream_t s);
+int elb200_zherk(char uplo, char trans, int64_t n, int64_t k, double alpha,
+                 const elb200_c64* A, int64_t lda, double beta, elb200_c64* C, int64_t ldc,
+                 elb200_stream_t s);
+int elb200_cherk(char uplo, char trans, int64_t n, int64_t k, float alpha,
+                 const elb200_c32* A, int64_t lda, float beta, elb200_c32* C, int64_t ldc,
+                 elb200_stream_t s);
+int elb200_zsyrk(char uplo, char trans, int64_t n, int64_t k, elb200_c64 alpha,
+                 const elb200_c64* A, int64_t lda, elb200_c64 beta, elb200_c64* C, int64_t ldc,
+                 elb200_stream_t s);
+int elb200_csyrk(char uplo, char trans, int64_t n, int64_t k, elb200_c32 alpha,
+                 const elb200_c32* A, int64_t lda, elb200_c32 beta, elb200_c32* C, int64_t ldc,
+                 elb200_stream_t s);
+
+/* ---- TRSM: B := alpha op(A)^-1 B (side 'L') or alpha B op(A)^-1 ('R') --- */
+int elb200_dtrsm(char side, char uplo, char trans, char diag, int64_t m, int64_t n,
+                 double alpha, const double* A, int64_t lda, double* B, int64_t ldb,
+                 elb200_stream_t s);
+int elb200_strsm(char side, char uplo, char trans, char diag, int64_t m, int64_t n,
+                 float alpha, const float* A, int64_t lda, float* B, int64_t ldb,
+                 elb200_stream_t s);
+int elb200_ztrsm(char side, char uplo, char trans, char diag, int64_t m, int64_t n,
+                 elb200_c64 alpha, const elb200_c64* A, int64_t lda, elb200_c64* B, int64_t ldb,
+                 elb200_stream_t s);
+int elb200_ctrsm(char side, char uplo, char trans, char diag, int64_t m, int64_t n,
+                 elb200_c32 alpha, const elb200_c32* A, int64_t lda, elb200_c32* B, int64_t ldb,
+                 elb200_stream_t s);
+
+/* ---- POTRF: unblocked-equivalent Cholesky of one n x n block ----------- */
+/* Factors the uplo triangle in place; the other triangle is not referenced.
+ * info_dev (device int, may not be NULL) is left untouched on success and
+ * receives j+1 for the first column j whose pivot is <= 0 or NaN (only if it
+ * still holds 0, so one flag can be shared by a whole factorisation).  The
+ * host layer turns a nonzero flag into NonHPDMatrixException
+ * (LowerVariant3.hpp:29-30). */
+int elb200_dpotrf(char uplo, int64_t n, double* A, int64_t lda, int* info_dev, elb200_stream_t s);
+int elb200_spotrf(char uplo, int64_t n, float* A, int64_t lda, int* info_dev, elb200_stream_t s);
+int elb200_zpotrf(char uplo, int64_t n, elb200_c64* A, int64_t lda, int* info_dev, elb200_stream_t s);
+int elb200_cpotrf(char uplo, int64_t n, elb200_c32* A, int64_t lda, int* info_dev, elb200_stream_t s);
+
+/* ---- FP64 tensor-pipe ceiling probe ------------------------------------ */
+/* Runs a register-resident DMMA (mma.sync m8n8k4 f64) loop on every SM and
+ * returns the achieved FLOP/s through *flops_per_s: the measured FP64 tensor
+ * roofline denominator used by bench.py. */
+int elb200_dmma_peak(int iters, double* flops_per_s, float* ms);
+
+/* ---- Fortran-77 BLAS ABI (device pointers, layer's current stream) ----- */
+/* Prototypes follow the reference's own declarations:
+ *   src/core/imports/blas/Gemm.hpp:13-40, Trsm.hpp:12-33, Syrk.hpp:12-50 */
+void sgemm_(const char* transA, const char* transB, const int* m, const int* n, const int* k,
+            const float* alpha, const float* A, const int* lda, const float* B, const int* ldb,
+            const float* beta, float* C, const int* ldc);
+void dgemm_(const char* transA, const char* transB, const int* m, const int* n, const int* k,
+            const double* alpha, const double* A, const int* lda, const double* B, const int* ldb,
+            const double* beta, double* C, const int* ldc);
+void cgemm_(const char* transA, const char* transB, const int* m, const int* n, const int* k,
+            const elb200_c32* alpha, const elb200_c32* A, const int* lda, const elb200_c32* B,
+            const int* ldb, const elb200_c32* beta, elb200_c32* C, const int* ldc);
+void zgemm_(const char* transA, const char* transB, const int* m, const int* n, const int* k,
+            const elb200_c64* alpha, const elb200_c64* A, const int* lda, const elb200_c64* B,
+            const int* ldb, const elb200_c64* beta, elb200_c64* C, const int* ldc);
+void strsm_(const char* side, const char* uplo, const char* trans, const char* diag,
+            const int* m, const int* n, const float* alpha, const float* A, const int* lda,
+            float* B, const int* ldb);
+void dtrsm_(const char* side, const char* uplo, const char* trans, const char* diag,
+            const int* m, const int* n, const double* alpha, const double* A, const int* lda,
+            double* B, const int* ldb);
+void ctrsm_(const char* side, const char* uplo, const char* trans, const char* diag,
+            const int* m, const int* n, const elb200_c32* alpha, const elb200_c32* A,
+            const int* lda, elb200_c32* B, const int* ldb);
+void ztrsm_(const char* side, const char* uplo, const char* trans, const char* diag,
+            const int* m, const int* n, const elb200_c64* alpha, const elb200_c64* A,
+            const int* lda, elb200_c64* B, const int* ldb);
+void ssyrk_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha,
+            const float* A, const int* lda, const float* beta, float* C, const int* ldc);
+void dsyrk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha,
+            const double* A, const int* lda, const double* beta, double* C, const int* ldc);
+void csyrk_(const char* uplo, const char* trans, const int* n, const int* k,
+            const elb200_c32* alpha, const elb200_c32* A, const int* lda,
+            const elb200_c32* beta, elb200_c32* C, const int* ldc);
+void zsyrk_(const char* uplo, const char* trans, const int* n, const int* k,
+            const elb200_c64* alpha, const elb200_c64* A, const int* lda,
+            const elb200_c64* beta, elb200_c64* C, const int* ldc);
+void cherk_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha,
+            const elb200_c32* A, const int* lda, const float* beta, elb200_c32* C, const int* ldc);
+void zherk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha,
+            const elb200_c64* A, const int* lda, const double* beta, elb200_c64* C, const int* ldc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELB200_BLAS_H */
