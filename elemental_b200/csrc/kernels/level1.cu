@@ -1,0 +1,286 @@
+// Memory-bound helpers of the hot path: strided block moves (pack / unpack /
+// transpose / axpy / scale in one kernel), trapezoid scaling, counter-hash
+// fills and norm reductions.  See include/elb200_level1.h for what each one
+// replaces in the reference.  All of these are HBM-bound; they are written
+// for coalesced 32-wide row access with a padded shared-memory tile when the
+// source is read transposed.
+#include "../common.hpp"
+#include "cplx.cuh"
+#include "elb200_level1.h"
+
+namespace elb200 {
+namespace {
+
+constexpr int MAX_BATCH = 16;
+struct LatticeBatch {
+    elb200_lattice d[MAX_BATCH];
+    int n;
+};
+
+template <class T, bool CONJ>
+__global__ void __launch_bounds__(256) lattice_copy_kernel(const LatticeBatch b, const T alpha,
+                                                           const int has_alpha, const int acc) {
+    __shared__ T sm[32][33];
+    const elb200_lattice d = b.d[blockIdx.y];
+    const T* __restrict__ src = (const T*)d.src;
+    T* __restrict__ dst = (T*)d.dst;
+    const i64 tiles_r = (d.nrows + 31) / 32, tiles_c = (d.ncols + 31) / 32;
+    const i64 ntiles = tiles_r * tiles_c;
+    const bool row_fast = (d.s_rs <= d.s_cs);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const i64 t0 = (tile % tiles_r) * 32, u0 = (tile / tiles_r) * 32;
+        // read: fastest thread index follows the smaller source stride
+#pragma unroll
+        for (int k = ty; k < 32; k += 8) {
+            const i64 t = row_fast ? t0 + tx : t0 + k;
+            const i64 u = row_fast ? u0 + k : u0 + tx;
+            if (t < d.nrows && u < d.ncols) {
+                T v = src[d.s_off + t * d.s_rs + u * d.s_cs];
+                if (CONJ) v = scalar_traits<T>::conj(v);
+                if (row_fast) sm[k][tx] = v;  // sm[u][t]
+                else sm[tx][k] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = ty; k < 32; k += 8) {
+            const i64 t = t0 + tx, u = u0 + k;
+            if (t < d.nrows && u < d.ncols) {
+                T v = sm[k][tx];
+                if (has_alpha) v = alpha * v;
+                T* p = dst + d.d_off + t * d.d_rs + u * d.d_cs;
+                if (acc) v = *p + v;
+                *p = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <class T>
+void lattice_copy_t(const elb200_lattice* descs, int ndesc, int conj, const void* alpha, int acc,
+                    cudaStream_t s) {
+    T a = scalar_traits<T>::from_real(1);
+    int has_alpha = 0;
+    if (alpha) {
+        a = *(const T*)alpha;
+        has_alpha = scalar_traits<T>::is_one(a) ? 0 : 1;
+    }
+    const int cap = sm_count() * 8;
+    for (int base = 0; base < ndesc; base += MAX_BATCH) {
+        LatticeBatch b;
+        b.n = 0;
+        i64 maxtiles = 0;
+        for (int i = base; i < ndesc && b.n < MAX_BATCH; ++i) {
+            if (descs[i].nrows <= 0 || descs[i].ncols <= 0) continue;
+            b.d[b.n++] = descs[i];
+            i64 t = ceil_div(descs[i].nrows, 32) * ceil_div(descs[i].ncols, 32);
+            if (t > maxtiles) maxtiles = t;
+        }
+        if (b.n == 0) continue;
+        dim3 grid((unsigned)(maxtiles < cap ? maxtiles : cap), (unsigned)b.n);
+        if (conj && scalar_traits<T>::is_complex)
+            lattice_copy_kernel<T, true><<<grid, 256, 0, s>>>(b, a, has_alpha, acc);
+        else
+            lattice_copy_kernel<T, false><<<grid, 256, 0, s>>>(b, a, has_alpha, acc);
+        ELB_LAUNCH_CHECK();
+    }
+}
+
+// MODE 0: scale inside trapezoid; MODE 1: zero outside trapezoid
+template <class T, int MODE>
+__global__ void __launch_bounds__(256) trapezoid_kernel(T alpha, int lower, i64 m, i64 n, T* A, i64 lda,
+                                                        i64 gi0, i64 gis, i64 gj0, i64 gjs, i64 offset) {
+    const i64 i = (i64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= m) return;
+    const i64 gi = gi0 + i * gis;
+    for (i64 j = blockIdx.y; j < n; j += gridDim.y) {
+        const i64 gj = gj0 + j * gjs;
+        const bool inside = lower ? (gj - gi <= offset) : (gj - gi >= offset);
+        T* p = A + i + j * lda;
+        if (MODE == 0) {
+            if (inside) *p = alpha * (*p);
+        } else {
+            if (!inside) *p = scalar_traits<T>::zero();
+        }
+    }
+}
+
+template <class T, int MODE>
+void trapezoid_t(const void* alpha, char uplo, i64 m, i64 n, void* A, i64 lda, i64 gi0, i64 gis,
+                 i64 gj0, i64 gjs, i64 offset, cudaStream_t s) {
+    if (m <= 0 || n <= 0) return;
+    const char u = up(uplo);
+    if (u != 'L' && u != 'U') throw std::logic_error("trapezoid: uplo must be 'L' or 'U'");
+    T a = alpha ? *(const T*)alpha : scalar_traits<T>::from_real(1);
+    dim3 grid((unsigned)ceil_div(m, 256), (unsigned)(n < 1024 ? n : 1024));
+    trapezoid_kernel<T, MODE><<<grid, 256, 0, s>>>(a, u == 'L', m, n, (T*)A, lda, gi0, gis, gj0, gjs, offset);
+    ELB_LAUNCH_CHECK();
+}
+
+__host__ __device__ inline unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 30;
+    x *= 0xBF58476D1CE4E5B9ULL;
+    x ^= x >> 27;
+    x *= 0x94D049BB133111EBULL;
+    x ^= x >> 31;
+    return x;
+}
+// u(i,j;seed) in [-1,1); restated verbatim in oracle/generator.py
+__host__ __device__ inline double hash_uniform(unsigned long long i, unsigned long long j,
+                                               unsigned long long seed) {
+    unsigned long long x = mix64(seed + 0x9E3779B97F4A7C15ULL);
+    x = mix64(x ^ (i * 0xD1B54A32D192ED03ULL + 0x2545F4914F6CDD1DULL));
+    x = mix64(x ^ (j * 0x8CB92BA72F3D8DD7ULL + 0x9E6C63D0676A9A99ULL));
+    return (double)(x >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+
+template <class T>
+__device__ inline T make_entry(double re, double im);
+template <> __device__ inline float make_entry<float>(double re, double) { return (float)re; }
+template <> __device__ inline double make_entry<double>(double re, double) { return re; }
+template <> __device__ inline c32_t make_entry<c32_t>(double re, double im) { return mk((float)re, (float)im); }
+template <> __device__ inline c64_t make_entry<c64_t>(double re, double im) { return mk(re, im); }
+
+template <class T>
+__global__ void __launch_bounds__(256) fill_hash_kernel(int kind, i64 m, i64 n, T* A, i64 lda, i64 gi0,
+                                                        i64 gis, i64 gj0, i64 gjs,
+                                                        unsigned long long seed, double diag) {
+    const i64 i = (i64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= m) return;
+    const unsigned long long gi = (unsigned long long)(gi0 + i * gis);
+    for (i64 j = blockIdx.y; j < n; j += gridDim.y) {
+        const unsigned long long gj = (unsigned long long)(gj0 + j * gjs);
+        double re, im = 0.0;
+        if (kind == 0) {
+            re = hash_uniform(gi, gj, seed);
+            if (scalar_traits<T>::is_complex) im = hash_uniform(gi, gj, seed + 1);
+        } else {
+            const unsigned long long lo = gi < gj ? gi : gj, hi = gi < gj ? gj : gi;
+            re = hash_uniform(lo, hi, seed);
+            if (scalar_traits<T>::is_complex && gi != gj) {
+                im = hash_uniform(lo, hi, seed + 1);
+                if (gi > gj) im = -im;  // lower triangle holds the conjugate
+            }
+            if (gi == gj) re += diag;
+        }
+        A[i + j * lda] = make_entry<T>(re, im);
+    }
+}
+
+template <class T>
+void fill_hash_t(int kind, i64 m, i64 n, void* A, i64 lda, i64 gi0, i64 gis, i64 gj0, i64 gjs,
+                 unsigned long long seed, double diag, cudaStream_t s) {
+    if (m <= 0 || n <= 0) return;
+    dim3 grid((unsigned)ceil_div(m, 256), (unsigned)(n < 2048 ? n : 2048));
+    fill_hash_kernel<T><<<grid, 256, 0, s>>>(kind, m, n, (T*)A, lda, gi0, gis, gj0, gjs, seed, diag);
+    ELB_LAUNCH_CHECK();
+}
+
+__device__ inline void atomic_max_nonneg(double* addr, double v) {
+    // valid for non-negative doubles: their bit patterns order like integers
+    atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
+}
+
+// MODE 0: sum of squares; MODE 1: max abs
+template <class T, int MODE>
+__global__ void __launch_bounds__(256) reduce_kernel(i64 m, i64 n, const T* __restrict__ A, i64 lda,
+                                                     double* out) {
+    double acc = 0.0;
+    for (i64 j = blockIdx.y; j < n; j += gridDim.y)
+        for (i64 i = (i64)blockIdx.x * 256 + threadIdx.x; i < m; i += (i64)gridDim.x * 256) {
+            const double a2 = (double)scalar_traits<T>::abs2(A[i + j * lda]);
+            if (MODE == 0) acc += a2;
+            else acc = acc > a2 ? acc : a2;
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, acc, o);
+        if (MODE == 0) acc += other;
+        else acc = acc > other ? acc : other;
+    }
+    __shared__ double ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = ws[0];
+        for (int w = 1; w < 8; ++w) {
+            if (MODE == 0) r += ws[w];
+            else r = r > ws[w] ? r : ws[w];
+        }
+        if (MODE == 0) atomicAdd(out, r);
+        else atomic_max_nonneg(out, sqrt(r));
+    }
+}
+
+template <class T, int MODE>
+void reduce_t(i64 m, i64 n, const void* A, i64 lda, double* out, cudaStream_t s) {
+    if (m <= 0 || n <= 0) return;
+    i64 gx = ceil_div(m, 256);
+    if (gx > 64) gx = 64;
+    dim3 grid((unsigned)gx, (unsigned)(n < 256 ? n : 256));
+    reduce_kernel<T, MODE><<<grid, 256, 0, s>>>(m, n, (const T*)A, lda, out);
+    ELB_LAUNCH_CHECK();
+}
+
+#define DISPATCH_DTYPE(dtype, CALL)                                   \
+    switch (dtype) {                                                  \
+        case ELB200_F32: { typedef float T; CALL; } break;            \
+        case ELB200_F64: { typedef double T; CALL; } break;           \
+        case ELB200_C32: { typedef c32_t T; CALL; } break;            \
+        case ELB200_C64: { typedef c64_t T; CALL; } break;            \
+        default: throw std::logic_error("unknown dtype code");        \
+    }
+
+}  // namespace
+}  // namespace elb200
+
+extern "C" {
+using namespace elb200;
+
+int elb200_lattice_copy(int dtype, const elb200_lattice* descs, int ndesc, int conj,
+                        const void* alpha, int accumulate, elb200_stream_t s) {
+    return guarded([&] {
+        DISPATCH_DTYPE(dtype, (lattice_copy_t<T>(descs, ndesc, conj, alpha, accumulate, (cudaStream_t)s)));
+    });
+}
+
+int elb200_scale_trapezoid(int dtype, const void* alpha, char uplo, int64_t m, int64_t n, void* A,
+                           int64_t lda, int64_t rowShift, int64_t rowStride, int64_t colShift,
+                           int64_t colStride, int64_t offset, elb200_stream_t s) {
+    return guarded([&] {
+        DISPATCH_DTYPE(dtype, (trapezoid_t<T, 0>(alpha, uplo, m, n, A, lda, rowShift, rowStride, colShift,
+                                                 colStride, offset, (cudaStream_t)s)));
+    });
+}
+
+int elb200_make_trapezoidal(int dtype, char uplo, int64_t m, int64_t n, void* A, int64_t lda,
+                            int64_t rowShift, int64_t rowStride, int64_t colShift,
+                            int64_t colStride, int64_t offset, elb200_stream_t s) {
+    return guarded([&] {
+        DISPATCH_DTYPE(dtype, (trapezoid_t<T, 1>(nullptr, uplo, m, n, A, lda, rowShift, rowStride, colShift,
+                                                 colStride, offset, (cudaStream_t)s)));
+    });
+}
+
+int elb200_fill_hash(int dtype, int kind, int64_t m, int64_t n, void* A, int64_t lda,
+                     int64_t rowShift, int64_t rowStride, int64_t colShift, int64_t colStride,
+                     uint64_t seed, double diag, elb200_stream_t s) {
+    return guarded([&] {
+        DISPATCH_DTYPE(dtype, (fill_hash_t<T>(kind, m, n, A, lda, rowShift, rowStride, colShift, colStride,
+                                              seed, diag, (cudaStream_t)s)));
+    });
+}
+
+int elb200_sumsq(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, double* out_dev,
+                 elb200_stream_t s) {
+    return guarded([&] { DISPATCH_DTYPE(dtype, (reduce_t<T, 0>(m, n, A, lda, out_dev, (cudaStream_t)s))); });
+}
+
+int elb200_maxabs(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, double* out_dev,
+                  elb200_stream_t s) {
+    return guarded([&] { DISPATCH_DTYPE(dtype, (reduce_t<T, 1>(m, n, A, lda, out_dev, (cudaStream_t)s))); });
+}
+
+}  // extern "C"
