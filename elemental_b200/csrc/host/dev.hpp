@@ -1,0 +1,46 @@
+// Host-layer internals: mapping from El scalar types to the kernels' POD types,
+// NCCL error checking and the typed leaf wrappers the algorithms call.
+#pragma once
+#include <nccl.h>
+
+#include "../kernels/device_api.hpp"
+#include "elb200/core.hpp"
+#include "elb200_level1.h"
+
+namespace El {
+namespace dev {
+
+template <typename T> struct DevType;
+template <> struct DevType<float> { typedef float type; };
+template <> struct DevType<double> { typedef double type; };
+template <> struct DevType<Complex<float>> { typedef elb200::c32_t type; };
+template <> struct DevType<Complex<double>> { typedef elb200::c64_t type; };
+template <typename T> using D = typename DevType<T>::type;
+
+template <typename T> inline D<T> val(T x);
+template <> inline float val<float>(float x) { return x; }
+template <> inline double val<double>(double x) { return x; }
+template <> inline elb200::c32_t val<Complex<float>>(Complex<float> x) { return elb200::mk(x.real(), x.imag()); }
+template <> inline elb200::c64_t val<Complex<double>>(Complex<double> x) { return elb200::mk(x.real(), x.imag()); }
+
+template <typename T> inline D<T>* ptr(T* p) { return reinterpret_cast<D<T>*>(p); }
+template <typename T> inline const D<T>* ptr(const T* p) { return reinterpret_cast<const D<T>*>(p); }
+
+template <typename T> constexpr int Code() { return elb200::dtype_code<D<T>>::value; }
+
+inline cudaStream_t stream() { return (cudaStream_t)CurrentStream(); }
+
+inline void nccl_check(ncclResult_t r, const char* what, const char* file, int line) {
+    if (r != ncclSuccess) {
+        RuntimeError(std::string("NCCL error in ") + what + " at " + file + ":" + std::to_string(line) + ": " +
+                     ncclGetErrorString(r));
+    }
+}
+#define ELB_NCCL(x) ::El::dev::nccl_check((x), #x, __FILE__, __LINE__)
+
+inline void c_check(int rc, const char* what) {
+    if (rc != 0) RuntimeError(std::string(what) + ": " + elb200::last_error());
+}
+
+}  // namespace dev
+}  // namespace El

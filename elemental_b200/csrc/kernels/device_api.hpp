@@ -1,0 +1,56 @@
+// Internal typed entry points shared by the kernel translation units and the
+// C++ host layer.  T is one of float, double, cplx<float>, cplx<double>.
+#pragma once
+#include "../common.hpp"
+#include "cplx.cuh"
+
+namespace elb200 {
+
+// mode 0 = full GEMM, 1 = lower-triangle TRRK, 2 = upper-triangle TRRK.
+// Global index of local C(i,j) is (gi0 + i*gis, gj0 + j*gjs) (TRRK only).
+// transA/transB in {'N','T','C'}.
+template <class T>
+void gemm_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, T alpha, const T* A,
+                 i64 lda, const T* B, i64 ldb, T beta, T* C, i64 ldc, i64 gi0, i64 gis, i64 gj0,
+                 i64 gjs, cudaStream_t s);
+
+// FP64 DMMA kernel (gemm_f64.cu)
+void dgemm_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, double alpha,
+                  const double* A, i64 lda, const double* B, i64 ldb, double beta, double* C,
+                  i64 ldc, i64 gi0, i64 gis, i64 gj0, i64 gjs, cudaStream_t s);
+// Complex<double> DMMA kernel (gemm_c64.cu)
+void zgemm_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, c64_t alpha,
+                  const c64_t* A, i64 lda, const c64_t* B, i64 ldb, c64_t beta, c64_t* C, i64 ldc,
+                  i64 gi0, i64 gis, i64 gj0, i64 gjs, cudaStream_t s);
+// Generic SIMT kernel, any type (gemm_simt.cu)
+template <class T>
+void gemm_simt_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, T alpha, const T* A,
+                      i64 lda, const T* B, i64 ldb, T beta, T* C, i64 ldc, i64 gi0, i64 gis,
+                      i64 gj0, i64 gjs, cudaStream_t s);
+
+template <class T>
+void trsm_device(char side, char uplo, char trans, char diag, i64 m, i64 n, T alpha, const T* A,
+                 i64 lda, T* B, i64 ldb, cudaStream_t s);
+
+// info_dev: device int, set to col_offset + j + 1 on the first non-positive pivot (if still 0)
+template <class T>
+void potrf_device(char uplo, i64 n, T* A, i64 lda, int* info_dev, i64 col_offset, cudaStream_t s);
+
+// dst (op)= alpha*op(src) on one strided block (level1.cu)
+template <class T>
+void lattice_copy_device(const T* src, T* dst, i64 nrows, i64 ncols, i64 s_off, i64 s_rs, i64 s_cs,
+                         i64 d_off, i64 d_rs, i64 d_cs, bool conj, const T* alpha, bool accumulate,
+                         cudaStream_t s);
+
+// Stream-ordered scratch memory (cudaMallocAsync on the device's default pool,
+// release threshold raised so repeated panel-sized requests are served from cache)
+void* scratch_alloc(size_t bytes, cudaStream_t s);
+void scratch_free(void* p, cudaStream_t s);
+
+template <class T> struct dtype_code;
+template <> struct dtype_code<float> { static constexpr int value = 0; };
+template <> struct dtype_code<double> { static constexpr int value = 1; };
+template <> struct dtype_code<c32_t> { static constexpr int value = 2; };
+template <> struct dtype_code<c64_t> { static constexpr int value = 3; };
+
+}  // namespace elb200

@@ -7,6 +7,7 @@
 #include "../common.hpp"
 #include "cplx.cuh"
 #include "elb200_level1.h"
+#include "device_api.hpp"
 
 namespace elb200 {
 namespace {
@@ -22,8 +23,8 @@ __global__ void __launch_bounds__(256) lattice_copy_kernel(const LatticeBatch b,
                                                            const int has_alpha, const int acc) {
     __shared__ T sm[32][33];
     const elb200_lattice d = b.d[blockIdx.y];
-    const T* __restrict__ src = (const T*)d.src;
-    T* __restrict__ dst = (T*)d.dst;
+    const T* src = (const T*)d.src;  // may alias dst (in-place scale)
+    T* dst = (T*)d.dst;
     const i64 tiles_r = (d.nrows + 31) / 32, tiles_c = (d.ncols + 31) / 32;
     const i64 ntiles = tiles_r * tiles_c;
     const bool row_fast = (d.s_rs <= d.s_cs);
@@ -224,6 +225,24 @@ void reduce_t(i64 m, i64 n, const void* A, i64 lda, double* out, cudaStream_t s)
     ELB_LAUNCH_CHECK();
 }
 
+}  // namespace
+
+template <class T>
+void lattice_copy_device(const T* src, T* dst, i64 nrows, i64 ncols, i64 s_off, i64 s_rs, i64 s_cs,
+                         i64 d_off, i64 d_rs, i64 d_cs, bool conj, const T* alpha, bool accumulate,
+                         cudaStream_t s) {
+    elb200_lattice d;
+    d.src = src; d.dst = dst; d.nrows = nrows; d.ncols = ncols;
+    d.s_off = s_off; d.s_rs = s_rs; d.s_cs = s_cs;
+    d.d_off = d_off; d.d_rs = d_rs; d.d_cs = d_cs;
+    lattice_copy_t<T>(&d, 1, conj ? 1 : 0, alpha, accumulate ? 1 : 0, s);
+}
+template void lattice_copy_device<float>(const float*, float*, i64, i64, i64, i64, i64, i64, i64, i64, bool, const float*, bool, cudaStream_t);
+template void lattice_copy_device<double>(const double*, double*, i64, i64, i64, i64, i64, i64, i64, i64, bool, const double*, bool, cudaStream_t);
+template void lattice_copy_device<c32_t>(const c32_t*, c32_t*, i64, i64, i64, i64, i64, i64, i64, i64, bool, const c32_t*, bool, cudaStream_t);
+template void lattice_copy_device<c64_t>(const c64_t*, c64_t*, i64, i64, i64, i64, i64, i64, i64, i64, bool, const c64_t*, bool, cudaStream_t);
+
+namespace {
 #define DISPATCH_DTYPE(dtype, CALL)                                   \
     switch (dtype) {                                                  \
         case ELB200_F32: { typedef float T; CALL; } break;            \

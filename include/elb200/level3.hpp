@@ -1,0 +1,68 @@
+// elb200 host layer, part 2: the distributed level-3 routines of the hot path with the
+// reference's signatures (include/El/blas_like/level3.hpp:34-68 Gemm/LocalGemm, :85-124
+// Herk/Syrk, :455-477 Trsm/LocalTrsm, :551-590 Trrk/LocalTrrk).
+#pragma once
+#include "elb200/core.hpp"
+
+namespace El {
+
+// ---- Gemm: C := alpha op(A) op(B) + beta C (src/blas_like/level3/Gemm.cpp:19-133) ----
+template <typename T>
+void Gemm(Orientation orientA, Orientation orientB, T alpha, const Matrix<T>& A, const Matrix<T>& B, T beta,
+          Matrix<T>& C);
+template <typename T>
+void Gemm(Orientation orientA, Orientation orientB, T alpha, const Matrix<T>& A, const Matrix<T>& B, Matrix<T>& C);
+template <typename T>
+void Gemm(Orientation orientA, Orientation orientB, T alpha, const AbstractDistMatrix<T>& A,
+          const AbstractDistMatrix<T>& B, T beta, AbstractDistMatrix<T>& C, GemmAlgorithm alg = GEMM_DEFAULT);
+template <typename T>
+void Gemm(Orientation orientA, Orientation orientB, T alpha, const AbstractDistMatrix<T>& A,
+          const AbstractDistMatrix<T>& B, AbstractDistMatrix<T>& C, GemmAlgorithm alg = GEMM_DEFAULT);
+// local product of the LOCAL matrices of compatibly distributed operands (Gemm.cpp:135-259)
+template <typename T>
+void LocalGemm(Orientation orientA, Orientation orientB, T alpha, const AbstractDistMatrix<T>& A,
+               const AbstractDistMatrix<T>& B, T beta, AbstractDistMatrix<T>& C);
+template <typename T>
+void LocalGemm(Orientation orientA, Orientation orientB, T alpha, const AbstractDistMatrix<T>& A,
+               const AbstractDistMatrix<T>& B, AbstractDistMatrix<T>& C);
+// which SUMMA variant GEMM_DEFAULT resolves to (Gemm/NN.hpp:304-313)
+GemmAlgorithm GemmDefaultAlgorithm(Int m, Int n, Int k);
+
+// ---- Trrk: triangular rank-k update (src/blas_like/level3/Trrk.cpp, Trrk/Local.hpp) ----
+template <typename T>
+void Trrk(UpperOrLower uplo, Orientation orientA, Orientation orientB, T alpha, const Matrix<T>& A,
+          const Matrix<T>& B, T beta, Matrix<T>& C);
+template <typename T>
+void Trrk(UpperOrLower uplo, Orientation orientA, Orientation orientB, T alpha, const AbstractDistMatrix<T>& A,
+          const AbstractDistMatrix<T>& B, T beta, AbstractDistMatrix<T>& C);
+// C[MC,MR] triangle += alpha op(A_local) op(B_local) with the global staircase mask
+template <typename T>
+void LocalTrrk(UpperOrLower uplo, Orientation orientA, Orientation orientB, T alpha,
+               const AbstractDistMatrix<T>& A, const AbstractDistMatrix<T>& B, T beta, AbstractDistMatrix<T>& C);
+
+// ---- Herk / Syrk (src/blas_like/level3/Herk.cpp:14-57, Syrk.cpp:20-86) ----
+template <typename T>
+void Syrk(UpperOrLower uplo, Orientation orientation, T alpha, const Matrix<T>& A, T beta, Matrix<T>& C,
+          bool conjugate = false);
+template <typename T>
+void Syrk(UpperOrLower uplo, Orientation orientation, T alpha, const AbstractDistMatrix<T>& A, T beta,
+          AbstractDistMatrix<T>& C, bool conjugate = false);
+template <typename T>
+void Herk(UpperOrLower uplo, Orientation orientation, Base<T> alpha, const Matrix<T>& A, Base<T> beta, Matrix<T>& C);
+template <typename T>
+void Herk(UpperOrLower uplo, Orientation orientation, Base<T> alpha, const AbstractDistMatrix<T>& A, Base<T> beta,
+          AbstractDistMatrix<T>& C);
+
+// ---- Trsm (src/blas_like/level3/Trsm.cpp:24-398, Trsm/{LLN,LLT,LUN,LUT,RLN,RLT,RUN,RUT}.hpp) ----
+template <typename F>
+void Trsm(LeftOrRight side, UpperOrLower uplo, Orientation orientation, UnitOrNonUnit diag, F alpha,
+          const Matrix<F>& A, Matrix<F>& B, bool checkIfSingular = false);
+template <typename F>
+void Trsm(LeftOrRight side, UpperOrLower uplo, Orientation orientation, UnitOrNonUnit diag, F alpha,
+          const AbstractDistMatrix<F>& A, AbstractDistMatrix<F>& B, bool checkIfSingular = false,
+          TrsmAlgorithm alg = TRSM_DEFAULT);
+template <typename F>
+void LocalTrsm(LeftOrRight side, UpperOrLower uplo, Orientation orientation, UnitOrNonUnit diag, F alpha,
+               const AbstractDistMatrix<F>& A, AbstractDistMatrix<F>& X, bool checkIfSingular = false);
+
+}  // namespace El

@@ -1,0 +1,161 @@
+/*
+ * elb200_El.h -- the reference's C API for the Gemm / Cholesky / HPDSolve path, served by
+ * the B200-native layer.  Names, argument order and ElError convention follow the
+ * reference's own C headers so that a binding written against them (its Python ctypes
+ * package, python/) keeps working:
+ *   include/El/core/Grid.h:30-141, include/El/core/DistMatrix.h:58-,
+ *   include/El/blas_like/level1.h (ElCopyDist, ElTransposeDist ...),
+ *   include/El/blas_like/level3.h:29-92,575-704 (ElGemmDist, ElGemmXDist, ElHerkDist,
+ *   ElTrsmDist, ElTrrkDist), include/El/lapack_like/factor.h:29-32 (ElCholeskyDist),
+ *   include/El/lapack_like/solve.h:151-173 (ElHPDSolveDist),
+ *   include/El/core/environment.h (ElBlocksize, ElSetBlocksize, Push/Pop).
+ * Differences, all forced by the device: DistMatrix buffers are DEVICE pointers, a Grid is
+ * created from a broadcast ncclUniqueId instead of an MPI_Comm (ElGridCreateNccl), and
+ * complex scalars are passed as {re,im} structs.  Suffixes: _s float, _d double,
+ * _c complex<float>, _z complex<double>.
+ */
+#ifndef ELB200_EL_H
+#define ELB200_EL_H
+
+#include <stdbool.h>
+#include <stdint.h>
+#include "elb200_blas.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int ElInt;
+typedef enum {
+    EL_SUCCESS, EL_ALLOC_ERROR, EL_OUT_OF_BOUNDS_ERROR, EL_ARG_ERROR, EL_LOGIC_ERROR, EL_RUNTIME_ERROR,
+    EL_NON_HPD_ERROR = 100, EL_SINGULAR_ERROR = 101, /* extensions: reference maps these to EL_RUNTIME_ERROR */
+    EL_ERROR = -1
+} ElError;
+typedef enum { EL_MC, EL_MD, EL_MR, EL_VC, EL_VR, EL_STAR, EL_CIRC } ElDist;
+typedef enum { EL_NORMAL, EL_TRANSPOSE, EL_ADJOINT } ElOrientation;
+typedef enum { EL_LOWER, EL_UPPER } ElUpperOrLower;
+typedef enum { EL_LEFT, EL_RIGHT } ElLeftOrRight;
+typedef enum { EL_NON_UNIT, EL_UNIT } ElUnitOrNonUnit;
+typedef enum { EL_ROW_MAJOR, EL_COLUMN_MAJOR } ElGridOrderType;
+typedef enum { EL_GEMM_DEFAULT, EL_GEMM_SUMMA_A, EL_GEMM_SUMMA_B, EL_GEMM_SUMMA_C, EL_GEMM_SUMMA_DOT,
+               EL_GEMM_CANNON } ElGemmAlgorithm;
+
+typedef float ElScalar_s;
+typedef double ElScalar_d;
+typedef elb200_c32 ElScalar_c;
+typedef elb200_c64 ElScalar_z;
+
+typedef struct ElGrid_sDummy* ElGrid;
+typedef const struct ElGrid_sDummy* ElConstGrid;
+
+const char* ElErrorString(ElError error);
+const char* ElLastErrorMessage(void);
+
+/* environment */
+ElError ElInitialize(int* argc, char*** argv);
+ElError ElFinalize(void);
+ElError ElBlocksize(ElInt* blocksize);
+ElError ElSetBlocksize(ElInt blocksize);
+ElError ElPushBlocksizeStack(ElInt blocksize);
+ElError ElPopBlocksizeStack(void);
+ElError ElSetStream(elb200_stream_t stream);   /* stream all work is enqueued on */
+ElError ElSynchronize(void);
+
+/* Grid */
+ElError ElNcclUniqueId(void* out128);          /* rank 0 calls this and broadcasts the 128 bytes */
+ElError ElGridCreateNccl(const void* uniqueId128, int rank, int size, int height, ElGridOrderType order,
+                         ElGrid* grid);
+ElError ElGridCreateTrivial(ElGrid* grid);     /* single process, 1x1 */
+ElError ElGridDestroy(ElConstGrid grid);
+ElError ElGridHeight(ElConstGrid grid, int* height);
+ElError ElGridWidth(ElConstGrid grid, int* width);
+ElError ElGridSize(ElConstGrid grid, int* size);
+ElError ElGridRank(ElConstGrid grid, int* rank);
+ElError ElGridRow(ElConstGrid grid, int* row);
+ElError ElGridCol(ElConstGrid grid, int* col);
+ElError ElGridVCRank(ElConstGrid grid, int* rank);
+ElError ElGridVRRank(ElConstGrid grid, int* rank);
+
+/* redistribution-engine statistics since the last reset (copies, messages, bytesSent,
+ * packLaunches, zeroCopySends, reduceScatters, allGathers) */
+ElError ElRedistStats(uint64_t out[7], bool reset);
+
+#define ELB200_DECLARE_TYPE(SUF, SCALAR, REAL)                                                              \
+    typedef struct ElDistMatrix_##SUF##Dummy* ElDistMatrix_##SUF;                                           \
+    typedef const struct ElDistMatrix_##SUF##Dummy* ElConstDistMatrix_##SUF;                                \
+    ElError ElDistMatrixCreateSpecific_##SUF(ElDist U, ElDist V, ElConstGrid g, ElDistMatrix_##SUF* A);     \
+    ElError ElDistMatrixDestroy_##SUF(ElConstDistMatrix_##SUF A);                                           \
+    ElError ElDistMatrixEmpty_##SUF(ElDistMatrix_##SUF A);                                                  \
+    ElError ElDistMatrixResize_##SUF(ElDistMatrix_##SUF A, ElInt height, ElInt width);                      \
+    ElError ElDistMatrixAlign_##SUF(ElDistMatrix_##SUF A, int colAlign, int rowAlign, bool constrain);      \
+    ElError ElDistMatrixAlignWith_##SUF(ElDistMatrix_##SUF A, ElConstDistMatrix_##SUF B);                   \
+    ElError ElDistMatrixAttach_##SUF(ElDistMatrix_##SUF A, ElInt height, ElInt width, ElConstGrid g,        \
+                                     int colAlign, int rowAlign, SCALAR* deviceBuffer, ElInt ldim, int root); \
+    ElError ElDistMatrixLockedAttach_##SUF(ElDistMatrix_##SUF A, ElInt height, ElInt width, ElConstGrid g,  \
+                                           int colAlign, int rowAlign, const SCALAR* deviceBuffer,          \
+                                           ElInt ldim, int root);                                           \
+    ElError ElDistMatrixView_##SUF(ElDistMatrix_##SUF A, ElDistMatrix_##SUF parent, ElInt i, ElInt j,       \
+                                   ElInt height, ElInt width);                                              \
+    ElError ElDistMatrixHeight_##SUF(ElConstDistMatrix_##SUF A, ElInt* v);                                  \
+    ElError ElDistMatrixWidth_##SUF(ElConstDistMatrix_##SUF A, ElInt* v);                                   \
+    ElError ElDistMatrixLocalHeight_##SUF(ElConstDistMatrix_##SUF A, ElInt* v);                             \
+    ElError ElDistMatrixLocalWidth_##SUF(ElConstDistMatrix_##SUF A, ElInt* v);                              \
+    ElError ElDistMatrixLDim_##SUF(ElConstDistMatrix_##SUF A, ElInt* v);                                    \
+    ElError ElDistMatrixColAlign_##SUF(ElConstDistMatrix_##SUF A, int* v);                                  \
+    ElError ElDistMatrixRowAlign_##SUF(ElConstDistMatrix_##SUF A, int* v);                                  \
+    ElError ElDistMatrixColShift_##SUF(ElConstDistMatrix_##SUF A, int* v);                                  \
+    ElError ElDistMatrixRowShift_##SUF(ElConstDistMatrix_##SUF A, int* v);                                  \
+    ElError ElDistMatrixColStride_##SUF(ElConstDistMatrix_##SUF A, int* v);                                 \
+    ElError ElDistMatrixRowStride_##SUF(ElConstDistMatrix_##SUF A, int* v);                                 \
+    ElError ElDistMatrixBuffer_##SUF(ElDistMatrix_##SUF A, SCALAR** deviceBuffer);                          \
+    ElError ElDistMatrixLockedBuffer_##SUF(ElConstDistMatrix_##SUF A, const SCALAR** deviceBuffer);         \
+    /* whole local matrix <-> host column-major buffer (synchronous) */                                     \
+    ElError ElDistMatrixLocalToHost_##SUF(ElConstDistMatrix_##SUF A, SCALAR* host, ElInt hostLDim);         \
+    ElError ElDistMatrixLocalFromHost_##SUF(ElDistMatrix_##SUF A, const SCALAR* host, ElInt hostLDim);      \
+    ElError ElDistMatrixHashFill_##SUF(ElDistMatrix_##SUF A, int kind, uint64_t seed, double diag);         \
+    /* level 1 */                                                                                           \
+    ElError ElCopyDist_##SUF(ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B);                              \
+    ElError ElTransposeDist_##SUF(ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B);                         \
+    ElError ElAdjointDist_##SUF(ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B);                           \
+    ElError ElAxpyDist_##SUF(SCALAR alpha, ElConstDistMatrix_##SUF X, ElDistMatrix_##SUF Y);                \
+    ElError ElAxpyContractDist_##SUF(SCALAR alpha, ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B);        \
+    ElError ElContractDist_##SUF(ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B);                          \
+    ElError ElScaleDist_##SUF(SCALAR alpha, ElDistMatrix_##SUF A);                                          \
+    ElError ElZeroDist_##SUF(ElDistMatrix_##SUF A);                                                         \
+    ElError ElScaleTrapezoidDist_##SUF(SCALAR alpha, ElUpperOrLower uplo, ElDistMatrix_##SUF A, ElInt offset); \
+    ElError ElMakeTrapezoidalDist_##SUF(ElUpperOrLower uplo, ElDistMatrix_##SUF A, ElInt offset);           \
+    ElError ElFrobeniusNormDist_##SUF(ElConstDistMatrix_##SUF A, REAL* norm);                               \
+    ElError ElMaxNormDist_##SUF(ElConstDistMatrix_##SUF A, REAL* norm);                                     \
+    /* level 3 */                                                                                           \
+    ElError ElGemmDist_##SUF(ElOrientation orientationOfA, ElOrientation orientationOfB, SCALAR alpha,      \
+                             ElConstDistMatrix_##SUF A, ElConstDistMatrix_##SUF B, SCALAR beta,             \
+                             ElDistMatrix_##SUF C);                                                         \
+    ElError ElGemmXDist_##SUF(ElOrientation orientationOfA, ElOrientation orientationOfB, SCALAR alpha,     \
+                              ElConstDistMatrix_##SUF A, ElConstDistMatrix_##SUF B, SCALAR beta,            \
+                              ElDistMatrix_##SUF C, ElGemmAlgorithm alg);                                   \
+    ElError ElSyrkDist_##SUF(ElUpperOrLower uplo, ElOrientation orientation, SCALAR alpha,                  \
+                             ElConstDistMatrix_##SUF A, SCALAR beta, ElDistMatrix_##SUF C);                 \
+    ElError ElHerkDist_##SUF(ElUpperOrLower uplo, ElOrientation orientation, REAL alpha,                    \
+                             ElConstDistMatrix_##SUF A, REAL beta, ElDistMatrix_##SUF C);                   \
+    ElError ElTrrkDist_##SUF(ElUpperOrLower uplo, ElOrientation orientationOfA, ElOrientation orientationOfB, \
+                             SCALAR alpha, ElConstDistMatrix_##SUF A, ElConstDistMatrix_##SUF B, SCALAR beta, \
+                             ElDistMatrix_##SUF C);                                                         \
+    ElError ElTrsmDist_##SUF(ElLeftOrRight side, ElUpperOrLower uplo, ElOrientation orientation,            \
+                             ElUnitOrNonUnit diag, SCALAR alpha, ElConstDistMatrix_##SUF A,                 \
+                             ElDistMatrix_##SUF B);                                                         \
+    /* factor / solve */                                                                                    \
+    ElError ElCholeskyDist_##SUF(ElUpperOrLower uplo, ElDistMatrix_##SUF A);                                \
+    ElError ElCholeskySolveAfterDist_##SUF(ElUpperOrLower uplo, ElOrientation orientation,                  \
+                                           ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B);                \
+    ElError ElHPDSolveDist_##SUF(ElUpperOrLower uplo, ElOrientation orientation, ElConstDistMatrix_##SUF A, \
+                                 ElDistMatrix_##SUF B);
+
+ELB200_DECLARE_TYPE(s, float, float)
+ELB200_DECLARE_TYPE(d, double, double)
+ELB200_DECLARE_TYPE(c, elb200_c32, float)
+ELB200_DECLARE_TYPE(z, elb200_c64, double)
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,136 @@
+"""ctypes wrapper over oracle/_ref/libElRef.so -- the REFERENCE itself (Elemental's own
+sources, built by oracle/refbuild/Makefile).  TEST INFRASTRUCTURE ONLY: used to pin
+oracle/elemental_oracle.py, to generate tests/golden/, and as bench.py's CPU baseline."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+REF_LIB = Path(__file__).resolve().parent / "_ref" / "libElRef.so"
+_lib = None
+
+
+class ReferenceUnavailable(RuntimeError):
+    pass
+
+
+class RefNonHPD(Exception):
+    pass
+
+
+def available() -> bool:
+    return REF_LIB.exists()
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not REF_LIB.exists():
+            raise ReferenceUnavailable(f"{REF_LIB} not built (make -C oracle/refbuild)")
+        _lib = C.CDLL(str(REF_LIB))
+        _lib.elref_last_error.restype = C.c_char_p
+        _lib.elref_blas_corename.restype = C.c_char_p
+        _lib.elref_blas_config.restype = C.c_char_p
+    return _lib
+
+
+def _chk(rc):
+    if rc == 2:
+        raise RefNonHPD(lib().elref_last_error().decode())
+    if rc != 0:
+        raise RuntimeError("reference call failed: " + lib().elref_last_error().decode())
+
+
+_SUF = {np.dtype(np.float32): "s", np.dtype(np.float64): "d", np.dtype(np.complex64): "c",
+        np.dtype(np.complex128): "z"}
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f(a, dtype=None):
+    return np.asfortranarray(a, dtype=dtype)
+
+
+def _scalar(x, dt):
+    """real types pass by value, complex through a 2-element real array"""
+    if dt.kind == "c":
+        r = np.array([np.real(x), np.imag(x)], dtype=np.float64 if dt == np.complex128 else np.float32)
+        return r, _p(r)
+    return None, (C.c_double(float(x)) if dt == np.float64 else C.c_float(float(x)))
+
+
+def info():
+    L = lib()
+    return {"corename": L.elref_blas_corename().decode(), "threads": L.elref_get_threads(),
+            "config": L.elref_blas_config().decode()}
+
+
+def set_threads(n: int):
+    lib().elref_set_threads(int(n))
+
+
+def gemm(oa, ob, alpha, A, B, beta, Cm, nb=128, alg=0):
+    """El::Gemm on DistMatrix<T,MC,MR> over the 1x1 default grid (in place on Cm, Fortran order)."""
+    dt = Cm.dtype
+    A, B = _f(A, dt), _f(B, dt)
+    assert Cm.flags.f_contiguous
+    m, n = Cm.shape
+    k = A.shape[1] if oa.upper() == "N" else A.shape[0]
+    ka, av = _scalar(alpha, dt)
+    kb, bv = _scalar(beta, dt)
+    fn = getattr(lib(), "elref_gemm_" + _SUF[dt])
+    _chk(fn(C.c_char(oa.encode()), C.c_char(ob.encode()), m, n, k, av, _p(A), A.shape[0], _p(B), B.shape[0],
+            bv, _p(Cm), Cm.shape[0], int(nb), int(alg)))
+    return Cm
+
+
+def cholesky(uplo, A, nb=128):
+    assert A.flags.f_contiguous
+    fn = getattr(lib(), "elref_cholesky_" + _SUF[A.dtype])
+    _chk(fn(C.c_char(uplo.encode()), A.shape[0], _p(A), A.shape[0], int(nb)))
+    return A
+
+
+def hpd_solve(uplo, orient, A, B, nb=128):
+    assert B.flags.f_contiguous
+    A = _f(A, B.dtype)
+    fn = getattr(lib(), "elref_hpdsolve_" + _SUF[B.dtype])
+    _chk(fn(C.c_char(uplo.encode()), C.c_char(orient.encode()), A.shape[0], B.shape[1], _p(A), A.shape[0],
+            _p(B), B.shape[0], int(nb)))
+    return B
+
+
+def trsm(side, uplo, orient, diag, alpha, A, B, nb=128):
+    assert B.flags.f_contiguous
+    A = _f(A, B.dtype)
+    ka, av = _scalar(alpha, B.dtype)
+    fn = getattr(lib(), "elref_trsm_" + _SUF[B.dtype])
+    _chk(fn(C.c_char(side.encode()), C.c_char(uplo.encode()), C.c_char(orient.encode()), C.c_char(diag.encode()),
+            B.shape[0], B.shape[1], av, _p(A), A.shape[0], _p(B), B.shape[0], int(nb)))
+    return B
+
+
+def herk(uplo, orient, alpha, A, beta, Cm, nb=128):
+    assert Cm.flags.f_contiguous
+    A = _f(A, Cm.dtype)
+    n = Cm.shape[0]
+    k = A.shape[1] if orient.upper() == "N" else A.shape[0]
+    fn = getattr(lib(), "elref_herk_" + _SUF[Cm.dtype])
+    _chk(fn(C.c_char(uplo.encode()), C.c_char(orient.encode()), n, k, C.c_double(alpha), _p(A), A.shape[0],
+            C.c_double(beta), _p(Cm), n, int(nb)))
+    return Cm
+
+
+def trrk(uplo, oa, ob, alpha, A, B, beta, Cm, nb=128):
+    assert Cm.flags.f_contiguous and Cm.dtype == np.float64
+    A, B = _f(A, np.float64), _f(B, np.float64)
+    n = Cm.shape[0]
+    k = A.shape[1] if oa.upper() == "N" else A.shape[0]
+    _chk(lib().elref_trrk_d(C.c_char(uplo.encode()), C.c_char(oa.encode()), C.c_char(ob.encode()), n, k,
+                            C.c_double(alpha), _p(A), A.shape[0], _p(B), B.shape[0], C.c_double(beta), _p(Cm), n,
+                            int(nb)))
+    return Cm
