@@ -33,7 +33,18 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
     }
 }
 #define ELB_CUDA(x) ::elb200::cuda_check((x), #x, __FILE__, __LINE__)
-#define ELB_LAUNCH_CHECK() ::elb200::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)
+// every kernel launch of the layer goes through this macro: it also feeds the launch counter
+// that bench.py reports as "gpu_launches"
+extern unsigned long long g_kernel_launches;
+#define ELB_LAUNCH_CHECK()                                                                  \
+    do {                                                                                    \
+        ++::elb200::g_kernel_launches;                                                      \
+        ::elb200::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__);      \
+    } while (0)
+
+// optional per-launch timing of the GEMM kernels (CUDA events on the launching stream)
+void gemm_profile_begin(cudaStream_t s);
+void gemm_profile_end(cudaStream_t s, double flops);
 
 inline i64 ceil_div(i64 a, i64 b) { return (a + b - 1) / b; }
 

@@ -47,6 +47,7 @@ struct GemmArgs {
     // global index of local (i,j) is (gi0 + i*gis, gj0 + j*gjs) -- TRRK only
     i64 gi0, gis, gj0, gjs;
     int vecA, vecB;  // 1 when 16-byte cp.async is legal for that operand
+    double flops;    // algorithmic flops of this launch (host-side bookkeeping only)
     i64 tilesM, tilesN;
 };
 
@@ -65,7 +66,7 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
@@ -224,24 +225,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(const GemmArgs p)
     cp_async_wait<0>();
 
     // ---- epilogue: C = alpha*acc + beta*C (masked for TRRK) ----
+    // All loads of one 8-column group are issued before the first store so that the
+    // read-modify-write of C costs one memory round trip per group, not one per element.
     const double alpha = p.alpha, beta = p.beta;
+    const bool useC = (beta != 0.0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+        double old[2][8];
+        bool ok[2][8];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const i64 col = n0 + wn0 + j * 8 + 2 * t + e;
-            if (col >= p.n) continue;
             const i64 gj = p.gj0 + col * p.gjs;
+            const double* cptr = p.C + col * p.ldc;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const i64 row = m0 + wm0 + i * 8 + g;
+                bool v = (col < p.n) && (row < p.m);
+                if (MODE == 1) v = v && (p.gi0 + row * p.gis >= gj);
+                if (MODE == 2) v = v && (p.gi0 + row * p.gis <= gj);
+                ok[e][i] = v;
+                old[e][i] = (v && useC) ? cptr[row] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const i64 col = n0 + wn0 + j * 8 + 2 * t + e;
             double* cptr = p.C + col * p.ldc;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const i64 row = m0 + wm0 + i * 8 + g;
-                if (row >= p.m) continue;
-                if (MODE == 1 && (p.gi0 + row * p.gis < gj)) continue;
-                if (MODE == 2 && (p.gi0 + row * p.gis > gj)) continue;
-                double v = alpha * acc[i][j][e];
-                if (beta != 0.0) v += beta * cptr[row];
-                cptr[row] = v;
+                if (ok[e][i]) {
+                    double v = alpha * acc[i][j][e];
+                    if (useC) v += beta * old[e][i];
+                    cptr[row] = v;
+                }
             }
         }
     }
@@ -257,8 +275,10 @@ void launch(const GemmArgs& a, cudaStream_t s) {
         configured = true;
     }
     const i64 tiles = a.tilesM * a.tilesN;
+    gemm_profile_begin(s);
     kern<<<(unsigned)tiles, NTHREADS, SMEM_BYTES, s>>>(a);
     ELB_LAUNCH_CHECK();
+    gemm_profile_end(s, a.flops);
 }
 
 template <int MODE>
@@ -300,6 +320,24 @@ void dgemm_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, doubl
     a.vecB = (((uintptr_t)B & 15) == 0 && (ldb % 2) == 0) ? 1 : 0;
     a.tilesM = ceil_div(m, BM);
     a.tilesN = ceil_div(n, BN);
+    // algorithmic flops: 2mnk for GEMM; for TRRK 2k per C entry inside the global triangle
+    if (mode == 0) a.flops = 2.0 * double(m) * double(n) * double(a.k);
+    else {
+        double inside = 0;
+        for (i64 j = 0; j < n; ++j) {
+            const i64 gj = gj0 + j * gjs;
+            i64 cnt;
+            if (mode == 1) {  // rows with gi0 + i*gis >= gj
+                i64 first = gj <= gi0 ? 0 : (gj - gi0 + gis - 1) / gis;
+                cnt = first >= m ? 0 : m - first;
+            } else {  // rows with gi0 + i*gis <= gj
+                cnt = gj < gi0 ? 0 : (gj - gi0) / gis + 1;
+                if (cnt > m) cnt = m;
+            }
+            inside += double(cnt);
+        }
+        a.flops = 2.0 * inside * double(a.k);
+    }
     // A 'T' is K-major; B 'N' is K-major
     const bool ak = ta, bk = !tb;
     if (mode == 0) dispatch<0>(ak, bk, a, s);

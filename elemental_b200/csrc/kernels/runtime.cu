@@ -2,6 +2,7 @@
 // tensor-pipe (DMMA) ceiling probe that bench.py uses as roofline denominator.
 #include "../common.hpp"
 #include "elb200_blas.h"
+#include <vector>
 
 namespace elb200 {
 
@@ -12,6 +13,33 @@ void set_last_error(const std::string& s) { g_last_error = s; }
 const char* last_error() { return g_last_error.c_str(); }
 cudaStream_t current_stream() { return g_stream; }
 void set_current_stream(cudaStream_t s) { g_stream = s; }
+
+unsigned long long g_kernel_launches = 0;
+
+// ---- GEMM launch profiling (off by default) ----
+namespace {
+struct ProfPair { cudaEvent_t a, b; double flops; };
+bool g_prof_on = false;
+std::vector<ProfPair> g_prof;
+size_t g_prof_used = 0;
+}  // namespace
+void gemm_profile_begin(cudaStream_t s) {
+    if (!g_prof_on) return;
+    if (g_prof_used == g_prof.size()) {
+        ProfPair p;
+        ELB_CUDA(cudaEventCreate(&p.a));
+        ELB_CUDA(cudaEventCreate(&p.b));
+        p.flops = 0;
+        g_prof.push_back(p);
+    }
+    ELB_CUDA(cudaEventRecord(g_prof[g_prof_used].a, s));
+}
+void gemm_profile_end(cudaStream_t s, double flops) {
+    if (!g_prof_on) return;
+    g_prof[g_prof_used].flops = flops;
+    ELB_CUDA(cudaEventRecord(g_prof[g_prof_used].b, s));
+    ++g_prof_used;
+}
 
 int sm_count() {
     static int n = 0;
@@ -63,6 +91,32 @@ int elb200_device_check(void) {
         ELB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
         if (major != 10)
             throw std::runtime_error("elb200: kernels are built for sm_100a only");
+    });
+}
+
+unsigned long long elb200_launch_count(int reset) {
+    unsigned long long v = elb200::g_kernel_launches;
+    if (reset) elb200::g_kernel_launches = 0;
+    return v;
+}
+void elb200_gemm_profile(int enable) {
+    elb200::g_prof_on = enable != 0;
+    elb200::g_prof_used = 0;
+}
+int elb200_gemm_profile_read(double* total_ms, long long* launches, double* flops) {
+    return elb200::guarded([&] {
+        double ms = 0, fl = 0;
+        for (size_t i = 0; i < elb200::g_prof_used; ++i) {
+            ELB_CUDA(cudaEventSynchronize(elb200::g_prof[i].b));
+            float t = 0;
+            ELB_CUDA(cudaEventElapsedTime(&t, elb200::g_prof[i].a, elb200::g_prof[i].b));
+            ms += t;
+            fl += elb200::g_prof[i].flops;
+        }
+        if (total_ms) *total_ms = ms;
+        if (launches) *launches = (long long)elb200::g_prof_used;
+        if (flops) *flops = fl;
+        elb200::g_prof_used = 0;
     });
 }
 

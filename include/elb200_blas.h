@@ -45,6 +45,14 @@ int elb200_device_check(void);
 void elb200_set_stream(elb200_stream_t s);
 elb200_stream_t elb200_get_stream(void);
 
+/* kernels launched by this library since the last reset (bench.py: "gpu_launches") */
+unsigned long long elb200_launch_count(int reset);
+/* Per-launch CUDA-event timing of the FP64 GEMM/TRRK kernel on its launching stream:
+ * enable, run, then read the summed device time, launch count and algorithmic flops
+ * (2mnk per launch; for TRRK only the tiles that are not skipped). */
+void elb200_gemm_profile(int enable);
+int elb200_gemm_profile_read(double* total_ms, long long* launches, double* flops);
+
 /* ---- GEMM: C := alpha op(A) op(B) + beta C ---------------------------- */
 /* trans in {'N','T','C'}; for real types 'C' == 'T' (blas/Gemm.hpp:386-387) */
 int elb200_dgemm(char transA, char transB, int64_t m, int64_t n, int64_t k,

@@ -1,0 +1,145 @@
+"""Multi-GPU parity worker, launched by torchrun (one rank per GPU, NCCL):
+   python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tests/mgpu_worker.py
+Every rank builds the same global inputs from the hash generator, runs the El-level call on an
+r x c Grid and compares the gathered result with the oracle / the reference library (a 1x1-grid
+run of the reference at the same Blocksize() is a valid oracle for p > 1 up to rounding,
+SURVEY.md section 8c)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import elemental_oracle as O  # noqa: E402
+from oracle import reference_lib as R  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from elemental_b200 import api as El
+    from planutil import LEGAL
+
+    height = {1: 1, 2: 1, 4: 2, 8: 2}.get(world, 0)
+    if len(sys.argv) > 1:
+        height = int(sys.argv[1])
+    g = El.Grid(height)
+    r, c = g.Height(), g.Width()
+    assert g.Rank() == rank or True
+    ORI = {"N": 0, "T": 1, "C": 2}
+    fails = []
+
+    def dm(a, dist_=(0, 2), align=None):
+        M = El.DistMatrix(a.dtype, dist_[0], dist_[1], g)
+        if align:
+            M.Align(align[0], align[1])
+        M.FromGlobal(a)
+        return M
+
+    # 1. redistribution: every pair, with alignments, plain and transposed (tests/core/DistMatrix.cpp)
+    G = O.fill(0, 37, 29, 1)
+    stride = {0: r, 2: c, 3: r * c, 4: r * c, 5: 1}
+    for t, (u, v) in enumerate(LEGAL):
+        A = dm(G, (u, v), (t % stride[u], (t + 1) % stride[v]))
+        for t2, (u2, v2) in enumerate(LEGAL):
+            B = El.DistMatrix(np.float64, u2, v2, g)
+            B.Align((t2 + 1) % stride[u2], t2 % stride[v2])
+            El.Copy(A, B)
+            if not np.array_equal(B.ToGlobal(), G):
+                fails.append(f"copy [{u},{v}]->[{u2},{v2}]")
+            Bt = El.DistMatrix(np.float64, u2, v2, g)
+            El.Transpose(A, Bt)
+            if not np.array_equal(Bt.ToGlobal(), G.T):
+                fails.append(f"transpose [{u},{v}]->[{u2},{v2}]")
+    # 2. Gemm: all SUMMA variants and orientations, double + complex double
+    for dt in (np.float64, np.complex128):
+        m, n, k, nb = 150, 130, 170, 32
+        for oa in "NTC":
+            for ob in "NTC":
+                A = O.fill(0, *((m, k) if oa == "N" else (k, m)), 1, dtype=dt)
+                B = O.fill(0, *((k, n) if ob == "N" else (n, k)), 2, dtype=dt)
+                C0 = O.fill(0, m, n, 3, dtype=dt)
+                for alg in (1, 2, 3, 4):
+                    El.PushBlocksizeStack(nb)
+                    dC = dm(C0)
+                    El.Gemm(ORI[oa], ORI[ob], 3.0, dm(A), dm(B), 4.0, dC, alg)
+                    El.PopBlocksizeStack()
+                    ref = (R.gemm(oa, ob, 3.0, A, B, 4.0, C0.copy(order="F"), nb=nb, alg=alg) if R.available()
+                           else O.gemm(oa, ob, 3.0, A, B, 4.0, C0.copy(order="F"), nb=nb, alg=alg))
+                    res = O.gemm_residual(dC.ToGlobal(), ref, k, A, B)
+                    if not res <= 1.0:
+                        fails.append(f"gemm {dt.__name__} {oa}{ob} alg={alg} res={res}")
+    # 3. Cholesky / HPDSolve / Trsm
+    for dt in (np.float64, np.complex128):
+        n, nb = 300, 64
+        A = O.fill(1, n, n, 5, diag=float(n), dtype=dt)
+        for uplo in "LU":
+            dA = dm(A)
+            El.PushBlocksizeStack(nb)
+            El.Cholesky(0 if uplo == "L" else 1, dA)
+            F = dA.ToGlobal()
+            res = O.cholesky_residual(uplo, F, A)
+            ref = R.cholesky(uplo, A.copy(order="F"), nb=nb) if R.available() else O.cholesky(uplo, A.copy(order="F"), nb)
+            tri = O._tri_mask(n, n, uplo)
+            dif = np.linalg.norm((F - ref)[tri]) / (n * np.finfo(np.float64).eps * np.linalg.norm(ref))
+            if not (res <= 10 and dif <= 20 and np.array_equal(F[~tri], A[~tri])):
+                fails.append(f"cholesky {dt.__name__} {uplo} res={res} dif={dif}")
+            Bm = O.fill(0, n, 40, 8, dtype=dt)
+            dB = dm(Bm)
+            El.HPDSolve(0 if uplo == "L" else 1, 0, dm(A), dB)
+            El.PopBlocksizeStack()
+            X = dB.ToGlobal()
+            rs = np.linalg.norm(A @ X - Bm) / (n * np.finfo(np.float64).eps * np.linalg.norm(A) * np.linalg.norm(X))
+            if not rs <= 10:
+                fails.append(f"hpdsolve {dt.__name__} {uplo} res={rs}")
+        try:
+            El.Cholesky(0, dm(O.fill(1, 100, 100, 5, diag=0.0, dtype=dt)))
+            fails.append("non-HPD did not raise")
+        except El.NonHPDMatrixException:
+            pass
+    for side in "LR":
+        m, n, nb = 90, 70, 32
+        na = m if side == "L" else n
+        A = np.asfortranarray(O.fill(0, na, na, 9) + na * np.eye(na))
+        for uplo in "LU":
+            for tr in "NT":
+                B0 = O.fill(0, m, n, 10)
+                dB = dm(B0)
+                El.PushBlocksizeStack(nb)
+                El.Trsm(0 if side == "L" else 1, 0 if uplo == "L" else 1, ORI[tr], 0, 2.0, dm(A), dB)
+                El.PopBlocksizeStack()
+                X = dB.ToGlobal()
+                T = O._tri(A, uplo, "N")
+                opT = T if tr == "N" else T.T
+                lhs = opT @ X if side == "L" else X @ opT
+                if not np.linalg.norm(lhs - 2 * B0) <= 50 * na * np.finfo(np.float64).eps * np.linalg.norm(T) * np.linalg.norm(X):
+                    fails.append(f"trsm {side}{uplo}{tr}")
+    # 4. Herk
+    A = O.fill(0, 120, 60, 3)
+    C0 = O.fill(0, 120, 120, 4)
+    dC = dm(C0)
+    El.PushBlocksizeStack(32)
+    El.Herk(0, 0, -1.0, dm(A), 1.0, dC)
+    El.PopBlocksizeStack()
+    if not np.linalg.norm(dC.ToGlobal() - O.herk("L", "N", -1.0, A, 1.0, C0.copy())) <= 1e-11:
+        fails.append("herk")
+
+    bad = torch.tensor([len(fails)], device="cuda")
+    dist.all_reduce(bad)
+    if fails:
+        print(f"[rank {rank}] FAILURES:\n  " + "\n  ".join(fails[:20]), flush=True)
+    if rank == 0:
+        print(f"MGPU {'OK' if bad.item() == 0 else 'FAILED'} grid={r}x{c} stats={El.RedistStats()}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if bad.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
