@@ -22,11 +22,15 @@ void dgemm_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, doubl
 void zgemm_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, c64_t alpha,
                   const c64_t* A, i64 lda, const c64_t* B, i64 ldb, c64_t beta, c64_t* C, i64 ldc,
                   i64 gi0, i64 gis, i64 gj0, i64 gjs, cudaStream_t s);
+// same, optionally forcing a real diagonal (HERK semantics: Im(c_ii) := 0)
+void zgemm_device_ex(int mode, char transA, char transB, i64 m, i64 n, i64 k, c64_t alpha,
+                     const c64_t* A, i64 lda, const c64_t* B, i64 ldb, c64_t beta, c64_t* C, i64 ldc,
+                     i64 gi0, i64 gis, i64 gj0, i64 gjs, bool realDiag, cudaStream_t s);
 // Generic SIMT kernel, any type (gemm_simt.cu)
 template <class T>
 void gemm_simt_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, T alpha, const T* A,
                       i64 lda, const T* B, i64 ldb, T beta, T* C, i64 ldc, i64 gi0, i64 gis,
-                      i64 gj0, i64 gjs, cudaStream_t s);
+                      i64 gj0, i64 gjs, cudaStream_t s, bool realDiag = false);
 
 template <class T>
 void trsm_device(char side, char uplo, char trans, char diag, i64 m, i64 n, T alpha, const T* A,

@@ -23,17 +23,33 @@
 #include "elb200_blas.h"
 
 namespace elb200 {
+extern int g_dgemm_config;
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int STAGES = 4;
-constexpr int NTHREADS = 256;
-constexpr int LDMN = BM + 4;  // 132
-constexpr int LDK = BK + 4;   // 20
-constexpr int TILE_DOUBLES = (BM * LDK > BK * LDMN) ? BM * LDK : BK * LDMN;  // 2560
-constexpr int STAGE_DOUBLES = 2 * TILE_DOUBLES;
-constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;  // 163840
-constexpr int GROUP_N = 8;  // tile columns per rasterisation group
+constexpr int BK = 16;
+constexpr int LDK = BK + 4;   // K-major pitch (doubles), == 4 mod 16
+constexpr int GROUP_N = 8;    // tile columns per rasterisation group
+
+// Tile configuration.  Every warp owns a 64 x 32 sub-tile (8 x 4 m8n8k4 accumulators,
+// 64 doubles per lane); WM x WN warps make the CTA tile.
+//   Cfg128x128: 8 warps, 4 stages, 160 KB smem, one CTA per SM  -- best for long k
+//   Cfg128x64 : 4 warps, 3 stages,  90 KB smem, TWO CTAs per SM -- the two CTAs are not
+//               synchronised with each other, so one CTA's C read-modify-write epilogue and
+//               pipeline prologue overlap the other's DMMA main loop.  This is what makes the
+//               rank-nb updates (k = Blocksize() = 128..256) of SUMMA-C and Cholesky fast.
+template <int WM_, int WN_, int STAGES_, int MINB_>
+struct Cfg {
+    static constexpr int WM = WM_, WN = WN_, STAGES = STAGES_, MINB = MINB_;
+    static constexpr int BM = 64 * WM, BN = 32 * WN;
+    static constexpr int NT = 32 * WM * WN;
+    static constexpr int LDA_MN = BM + 4, LDB_MN = BN + 4;  // MN-major pitches, == 4 mod 16
+    static constexpr int A_TILE = (BM * LDK > BK * LDA_MN) ? BM * LDK : BK * LDA_MN;
+    static constexpr int B_TILE = (BN * LDK > BK * LDB_MN) ? BN * LDK : BK * LDB_MN;
+    static constexpr int STAGE_DOUBLES = A_TILE + B_TILE;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;
+};
+typedef Cfg<2, 4, 4, 1> Cfg128x128;
+typedef Cfg<2, 2, 3, 2> Cfg128x64;
 
 struct GemmArgs {
     i64 m, n, k;
@@ -67,24 +83,25 @@ __device__ __forceinline__ void cp_async_wait() {
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
 }
 
-// Stage one 128 x 16 operand tile.  X(r,kk) is the logical op(X) entry; R, K are
+// Stage one ROWS x 16 operand tile.  X(r,kk) is the logical op(X) entry; R, K are
 // the logical extents; rows beyond them are zero-filled (cp.async src-size 0).
-template <bool KMAJOR>
+template <bool KMAJOR, int ROWS, int NT>
 __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ X, i64 ld, i64 R,
                                           i64 K, i64 r0, i64 k0, int vec, int tid) {
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(s);
+    constexpr int LDMN = ROWS + 4;
     if (!KMAJOR) {
         // X(r,kk) at X[r + kk*ld]; smem s[kk*LDMN + r]
         if (vec) {
 #pragma unroll
-            for (int it = 0; it < (BK * BM / 2) / NTHREADS; ++it) {
-                int id = tid + it * NTHREADS;
-                int kk = id / (BM / 2);
-                int rr = (id % (BM / 2)) * 2;
+            for (int it = 0; it < (BK * ROWS / 2) / NT; ++it) {
+                int id = tid + it * NT;
+                int kk = id / (ROWS / 2);
+                int rr = (id % (ROWS / 2)) * 2;
                 i64 r = r0 + rr, kg = k0 + kk;
                 int valid = 0;
                 if (kg < K) {
@@ -96,10 +113,10 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
             }
         } else {
 #pragma unroll
-            for (int it = 0; it < (BK * BM) / NTHREADS; ++it) {
-                int id = tid + it * NTHREADS;
-                int kk = id / BM;
-                int rr = id % BM;
+            for (int it = 0; it < (BK * ROWS) / NT; ++it) {
+                int id = tid + it * NT;
+                int kk = id / ROWS;
+                int rr = id % ROWS;
                 i64 r = r0 + rr, kg = k0 + kk;
                 int valid = (kg < K && r < R) ? 8 : 0;
                 const double* src = valid ? (X + r + kg * ld) : X;
@@ -110,8 +127,8 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
         // X(r,kk) at X[kk + r*ld]; smem s[r*LDK + kk]
         if (vec) {
 #pragma unroll
-            for (int it = 0; it < (BM * BK / 2) / NTHREADS; ++it) {
-                int id = tid + it * NTHREADS;
+            for (int it = 0; it < (ROWS * BK / 2) / NT; ++it) {
+                int id = tid + it * NT;
                 int rr = id / (BK / 2);
                 int kk = (id % (BK / 2)) * 2;
                 i64 r = r0 + rr, kg = k0 + kk;
@@ -125,8 +142,8 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
             }
         } else {
 #pragma unroll
-            for (int it = 0; it < (BM * BK) / NTHREADS; ++it) {
-                int id = tid + it * NTHREADS;
+            for (int it = 0; it < (ROWS * BK) / NT; ++it) {
+                int id = tid + it * NT;
                 int rr = id / BK;
                 int kk = id % BK;
                 i64 r = r0 + rr, kg = k0 + kk;
@@ -138,15 +155,16 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
     }
 }
 
-template <bool KMAJOR>
+template <bool KMAJOR, int ROWS>
 __device__ __forceinline__ double frag(const double* s, int r, int kk) {
-    return KMAJOR ? s[r * LDK + kk] : s[kk * LDMN + r];
+    return KMAJOR ? s[r * LDK + kk] : s[kk * (ROWS + 4) + r];
 }
 
 // MODE 0: full GEMM; 1: lower-triangle TRRK; 2: upper-triangle TRRK
-template <bool A_KMAJOR, bool B_KMAJOR, int MODE>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(const GemmArgs p) {
+template <class CF, bool A_KMAJOR, bool B_KMAJOR, int MODE>
+__global__ void __launch_bounds__(CF::NT, CF::MINB) gemm_f64_kernel(const GemmArgs p) {
     extern __shared__ __align__(128) double smem[];
+    constexpr int BM = CF::BM, BN = CF::BN, STAGES = CF::STAGES, NT = CF::NT;
 
     // ---- tile coordinates (grouped rasterisation for L2 reuse) ----
     const i64 tile = blockIdx.x;
@@ -172,7 +190,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(const GemmArgs p)
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm0 = (warp & 1) * 64, wn0 = (warp >> 1) * 32;
+    const int wm0 = (warp % CF::WM) * 64, wn0 = (warp / CF::WM) * 32;
 
     double acc[8][4][2];
 #pragma unroll
@@ -186,10 +204,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(const GemmArgs p)
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < KT) {
-            double* sa = smem + s * STAGE_DOUBLES;
-            load_tile<A_KMAJOR>(sa, p.A, p.lda, p.m, p.k, m0, (i64)s * BK, p.vecA, tid);
-            load_tile<B_KMAJOR>(sa + TILE_DOUBLES, p.B, p.ldb, p.n, p.k, n0, (i64)s * BK, p.vecB,
-                                tid);
+            double* sa = smem + s * CF::STAGE_DOUBLES;
+            load_tile<A_KMAJOR, BM, NT>(sa, p.A, p.lda, p.m, p.k, m0, (i64)s * BK, p.vecA, tid);
+            load_tile<B_KMAJOR, BN, NT>(sa + CF::A_TILE, p.B, p.ldb, p.n, p.k, n0, (i64)s * BK, p.vecB, tid);
         }
         cp_async_commit();
     }
@@ -200,26 +217,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(const GemmArgs p)
         {
             const i64 nk = kt + STAGES - 1;
             if (nk < KT) {
-                double* sa = smem + (nk % STAGES) * STAGE_DOUBLES;
-                load_tile<A_KMAJOR>(sa, p.A, p.lda, p.m, p.k, m0, nk * BK, p.vecA, tid);
-                load_tile<B_KMAJOR>(sa + TILE_DOUBLES, p.B, p.ldb, p.n, p.k, n0, nk * BK, p.vecB,
-                                    tid);
+                double* sa = smem + (nk % STAGES) * CF::STAGE_DOUBLES;
+                load_tile<A_KMAJOR, BM, NT>(sa, p.A, p.lda, p.m, p.k, m0, nk * BK, p.vecA, tid);
+                load_tile<B_KMAJOR, BN, NT>(sa + CF::A_TILE, p.B, p.ldb, p.n, p.k, n0, nk * BK, p.vecB, tid);
             }
             cp_async_commit();
         }
-        const double* sa = smem + (kt % STAGES) * STAGE_DOUBLES;
-        const double* sb = sa + TILE_DOUBLES;
+        const double* sa = smem + (kt % STAGES) * CF::STAGE_DOUBLES;
+        const double* sb = sa + CF::A_TILE;
+        // register double-buffered fragments: the LDS of k-step ks+1 are in flight while the
+        // 32 DMMAs of k-step ks issue
+        double a[2][8], b[2][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[0][i] = frag<A_KMAJOR, BM>(sa, wm0 + i * 8 + g, t);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[0][j] = frag<B_KMAJOR, BN>(sb, wn0 + j * 8 + g, t);
 #pragma unroll
         for (int ks = 0; ks < BK / 4; ++ks) {
-            double a[8], b[4];
+            const int cur = ks & 1, nxt = cur ^ 1;
+            if (ks + 1 < BK / 4) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = frag<A_KMAJOR>(sa, wm0 + i * 8 + g, ks * 4 + t);
+                for (int i = 0; i < 8; ++i) a[nxt][i] = frag<A_KMAJOR, BM>(sa, wm0 + i * 8 + g, (ks + 1) * 4 + t);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = frag<B_KMAJOR>(sb, wn0 + j * 8 + g, ks * 4 + t);
+                for (int j = 0; j < 4; ++j) b[nxt][j] = frag<B_KMAJOR, BN>(sb, wn0 + j * 8 + g, (ks + 1) * 4 + t);
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[cur][i], b[cur][j]);
         }
     }
     cp_async_wait<0>();
@@ -265,31 +290,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(const GemmArgs p)
     }
 }
 
-template <bool AK, bool BK_, int MODE>
-void launch(const GemmArgs& a, cudaStream_t s) {
+template <class CF, bool AK, bool BK_, int MODE>
+void launch(GemmArgs a, cudaStream_t s) {
     static bool configured = false;
-    auto kern = gemm_f64_kernel<AK, BK_, MODE>;
+    auto kern = gemm_f64_kernel<CF, AK, BK_, MODE>;
     if (!configured) {
-        ELB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      SMEM_BYTES));
+        ELB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
+        ELB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
+    a.tilesM = ceil_div(a.m, CF::BM);
+    a.tilesN = ceil_div(a.n, CF::BN);
     const i64 tiles = a.tilesM * a.tilesN;
     gemm_profile_begin(s);
-    kern<<<(unsigned)tiles, NTHREADS, SMEM_BYTES, s>>>(a);
+    kern<<<(unsigned)tiles, CF::NT, CF::SMEM_BYTES, s>>>(a);
     ELB_LAUNCH_CHECK();
     gemm_profile_end(s, a.flops);
 }
 
+template <class CF, int MODE>
+void dispatch_cfg(bool ak, bool bk, const GemmArgs& a, cudaStream_t s) {
+    if (ak) {
+        if (bk) launch<CF, true, true, MODE>(a, s);
+        else launch<CF, true, false, MODE>(a, s);
+    } else {
+        if (bk) launch<CF, false, true, MODE>(a, s);
+        else launch<CF, false, false, MODE>(a, s);
+    }
+}
+
+
 template <int MODE>
 void dispatch(bool ak, bool bk, const GemmArgs& a, cudaStream_t s) {
-    if (ak) {
-        if (bk) launch<true, true, MODE>(a, s);
-        else launch<true, false, MODE>(a, s);
-    } else {
-        if (bk) launch<false, true, MODE>(a, s);
-        else launch<false, false, MODE>(a, s);
-    }
+    int cfg = g_dgemm_config;
+    if (cfg == 0) cfg = (a.k >= 2048) ? 1 : 2;
+    if (cfg == 1) dispatch_cfg<Cfg128x128, MODE>(ak, bk, a, s);
+    else dispatch_cfg<Cfg128x64, MODE>(ak, bk, a, s);
 }
 
 bool is_trans(char c, const char* what) {
@@ -300,6 +336,9 @@ bool is_trans(char c, const char* what) {
 }
 
 }  // namespace
+
+// tile configuration: 0 = automatic, 1 = force 128x128 (1 CTA/SM), 2 = force 128x64 (2 CTAs/SM)
+int g_dgemm_config = 0;
 
 // mode 0 = gemm, 1 = lower trrk, 2 = upper trrk
 void dgemm_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, double alpha,
@@ -318,8 +357,7 @@ void dgemm_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, doubl
     a.gi0 = gi0; a.gis = gis; a.gj0 = gj0; a.gjs = gjs;
     a.vecA = (((uintptr_t)A & 15) == 0 && (lda % 2) == 0) ? 1 : 0;
     a.vecB = (((uintptr_t)B & 15) == 0 && (ldb % 2) == 0) ? 1 : 0;
-    a.tilesM = ceil_div(m, BM);
-    a.tilesN = ceil_div(n, BN);
+    a.tilesM = a.tilesN = 0;  // set per tile configuration at launch
     // algorithmic flops: 2mnk for GEMM; for TRRK 2k per C entry inside the global triangle
     if (mode == 0) a.flops = 2.0 * double(m) * double(n) * double(a.k);
     else {
@@ -348,6 +386,8 @@ void dgemm_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, doubl
 }  // namespace elb200
 
 extern "C" {
+
+void elb200_dgemm_set_config(int cfg) { elb200::g_dgemm_config = cfg; }
 
 int elb200_dgemm(char transA, char transB, int64_t m, int64_t n, int64_t k, double alpha,
                  const double* A, int64_t lda, const double* B, int64_t ldb, double beta,

@@ -21,6 +21,7 @@ struct SimtArgs {
     i64 gi0, gis, gj0, gjs;
     int ta, tb;  // 0 N, 1 T, 2 C
     int mode;
+    int realDiag;  // HERK: force Im(c_ii) = 0
 };
 
 template <class T>
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtArgs p, T alpha, T b
             T* c = C + row + col * p.ldc;
             T v = alpha * acc[x][y];
             if (has_beta) v += beta * (*c);
+            if (p.realDiag && gi == gj) v = scalar_traits<T>::from_real(scalar_traits<T>::real_part(v));
             *c = v;
         }
     }
@@ -118,9 +120,10 @@ int trans_code(char c, const char* what) {
 template <class T>
 void gemm_simt_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, T alpha, const T* A,
                       i64 lda, const T* B, i64 ldb, T beta, T* C, i64 ldc, i64 gi0, i64 gis,
-                      i64 gj0, i64 gjs, cudaStream_t s) {
+                      i64 gj0, i64 gjs, cudaStream_t s, bool realDiag) {
     if (m < 0 || n < 0 || k < 0) throw std::logic_error("gemm: negative dimension");
     SimtArgs p;
+    p.realDiag = realDiag ? 1 : 0;
     p.ta = trans_code(transA, "A");
     p.tb = trans_code(transB, "B");
     if (!scalar_traits<T>::is_complex) {
@@ -138,14 +141,13 @@ void gemm_simt_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, T
     ELB_LAUNCH_CHECK();
 }
 
-template void gemm_simt_device<float>(int, char, char, i64, i64, i64, float, const float*, i64,
-                                      const float*, i64, float, float*, i64, i64, i64, i64, i64, cudaStream_t);
-template void gemm_simt_device<double>(int, char, char, i64, i64, i64, double, const double*, i64,
-                                       const double*, i64, double, double*, i64, i64, i64, i64, i64, cudaStream_t);
-template void gemm_simt_device<c32_t>(int, char, char, i64, i64, i64, c32_t, const c32_t*, i64,
-                                      const c32_t*, i64, c32_t, c32_t*, i64, i64, i64, i64, i64, cudaStream_t);
-template void gemm_simt_device<c64_t>(int, char, char, i64, i64, i64, c64_t, const c64_t*, i64,
-                                      const c64_t*, i64, c64_t, c64_t*, i64, i64, i64, i64, i64, cudaStream_t);
+#define ELB_SIMT_INST(T)                                                                                   \
+    template void gemm_simt_device<T>(int, char, char, i64, i64, i64, T, const T*, i64, const T*, i64, T, T*, \
+                                      i64, i64, i64, i64, i64, cudaStream_t, bool);
+ELB_SIMT_INST(float)
+ELB_SIMT_INST(double)
+ELB_SIMT_INST(c32_t)
+ELB_SIMT_INST(c64_t)
 
 // ---- typed dispatch -------------------------------------------------------
 template <>
@@ -194,6 +196,12 @@ int elb200_sgemm(char ta, char tb, int64_t m, int64_t n, int64_t k, float alpha,
     return guarded([&] {
         gemm_device<float>(0, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, 1, 0, 1, (cudaStream_t)s);
     });
+}
+// PLACEHOLDER until gemm_tf32.cu (tcgen05 kind::tf32, 3xTF32 split) lands: fails loudly, never
+// silently substitutes another kernel.
+int elb200_sgemm_3xtf32(char, char, int64_t, int64_t, int64_t, float, const float*, int64_t, const float*, int64_t,
+                        float, float*, int64_t, elb200_stream_t) {
+    return guarded([] { throw std::runtime_error("elb200_sgemm_3xtf32: the tcgen05 3xTF32 kernel is not built yet"); });
 }
 int elb200_zgemm(char ta, char tb, int64_t m, int64_t n, int64_t k, elb200_c64 alpha,
                  const elb200_c64* A, int64_t lda, const elb200_c64* B, int64_t ldb, elb200_c64 beta,
@@ -255,18 +263,18 @@ int elb200_zherk(char uplo, char trans, int64_t n, int64_t k, double alpha, cons
                  int64_t lda, double beta, elb200_c64* C, int64_t ldc, elb200_stream_t s) {
     return guarded([&] {
         const bool tr = up(trans) != 'N';
-        gemm_device<c64_t>(uplo_mode(uplo, "zherk"), tr ? 'C' : 'N', tr ? 'N' : 'C', n, n, k, mk(alpha, 0.0),
-                           (const c64_t*)A, lda, (const c64_t*)A, lda, mk(beta, 0.0), (c64_t*)C, ldc, 0, 1, 0,
-                           1, (cudaStream_t)s);
+        zgemm_device_ex(uplo_mode(uplo, "zherk"), tr ? 'C' : 'N', tr ? 'N' : 'C', n, n, k, mk(alpha, 0.0),
+                        (const c64_t*)A, lda, (const c64_t*)A, lda, mk(beta, 0.0), (c64_t*)C, ldc, 0, 1, 0, 1, true,
+                        (cudaStream_t)s);
     });
 }
 int elb200_cherk(char uplo, char trans, int64_t n, int64_t k, float alpha, const elb200_c32* A,
                  int64_t lda, float beta, elb200_c32* C, int64_t ldc, elb200_stream_t s) {
     return guarded([&] {
         const bool tr = up(trans) != 'N';
-        gemm_device<c32_t>(uplo_mode(uplo, "cherk"), tr ? 'C' : 'N', tr ? 'N' : 'C', n, n, k, mk(alpha, 0.f),
-                           (const c32_t*)A, lda, (const c32_t*)A, lda, mk(beta, 0.f), (c32_t*)C, ldc, 0, 1, 0,
-                           1, (cudaStream_t)s);
+        gemm_simt_device<c32_t>(uplo_mode(uplo, "cherk"), tr ? 'C' : 'N', tr ? 'N' : 'C', n, n, k, mk(alpha, 0.f),
+                                (const c32_t*)A, lda, (const c32_t*)A, lda, mk(beta, 0.f), (c32_t*)C, ldc, 0, 1, 0, 1,
+                                (cudaStream_t)s, true);
     });
 }
 int elb200_zsyrk(char uplo, char trans, int64_t n, int64_t k, elb200_c64 alpha, const elb200_c64* A,

@@ -53,6 +53,10 @@ unsigned long long elb200_launch_count(int reset);
 void elb200_gemm_profile(int enable);
 int elb200_gemm_profile_read(double* total_ms, long long* launches, double* flops);
 
+/* FP64 GEMM tile configuration: 0 automatic (default), 1 = 128x128 CTA tile, one CTA per SM,
+ * 2 = 128x64 CTA tile, two CTAs per SM (epilogue of one overlaps the main loop of the other) */
+void elb200_dgemm_set_config(int cfg);
+
 /* ---- GEMM: C := alpha op(A) op(B) + beta C ---------------------------- */
 /* trans in {'N','T','C'}; for real types 'C' == 'T' (blas/Gemm.hpp:386-387) */
 int elb200_dgemm(char transA, char transB, int64_t m, int64_t n, int64_t k,
