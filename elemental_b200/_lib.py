@@ -1,7 +1,7 @@
 """ctypes loader for libelb200.so.
 
 The product path has no CPU fallback: if the library is missing or no sm_100
-device is visible, the calls raise.  Nothing under oracle/ is imported here.
+device is visible, the calls raise.  The checker package (the CPU oracle) is never imported here.
 """
 from __future__ import annotations
 
