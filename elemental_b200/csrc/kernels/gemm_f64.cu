@@ -24,6 +24,11 @@
 
 namespace elb200 {
 extern int g_dgemm_config;
+extern int g_dgemm_last_kernel;
+// gemm_f64_tma.cu: persistent warp-specialised TMA kernel; false when the operands are not TMA-eligible
+bool dgemm_tma_device(int mode, bool ta, bool tb, i64 m, i64 n, i64 k, double alpha, const double* A, i64 lda,
+                      const double* B, i64 ldb, double beta, double* C, i64 ldc, i64 gi0, i64 gis, i64 gj0, i64 gjs,
+                      double flops, cudaStream_t s);
 namespace {
 
 constexpr int BK = 16;
@@ -323,7 +328,7 @@ void dispatch_cfg(bool ak, bool bk, const GemmArgs& a, cudaStream_t s) {
 template <int MODE>
 void dispatch(bool ak, bool bk, const GemmArgs& a, cudaStream_t s) {
     int cfg = g_dgemm_config;
-    if (cfg == 0) cfg = (a.k >= 2048) ? 1 : 2;
+    if (cfg == 0 || cfg == 3) cfg = 2;  // 2 CTAs/SM measured faster than 128x128 at every k (profiles/r01_probe2_v0.txt)
     if (cfg == 1) dispatch_cfg<Cfg128x128, MODE>(ak, bk, a, s);
     else dispatch_cfg<Cfg128x64, MODE>(ak, bk, a, s);
 }
@@ -337,8 +342,10 @@ bool is_trans(char c, const char* what) {
 
 }  // namespace
 
-// tile configuration: 0 = automatic, 1 = force 128x128 (1 CTA/SM), 2 = force 128x64 (2 CTAs/SM)
+// kernel selection: 0 = automatic (TMA kernel when eligible), 1 = cp.async 128x128 (1 CTA/SM),
+// 2 = cp.async 128x64 (2 CTAs/SM), 3 = TMA kernel when eligible else automatic cp.async
 int g_dgemm_config = 0;
+int g_dgemm_last_kernel = 0;  // 1 = cp.async kernel, 2 = persistent TMA kernel (tests assert on it)
 
 // mode 0 = gemm, 1 = lower trrk, 2 = upper trrk
 void dgemm_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, double alpha,
@@ -376,6 +383,16 @@ void dgemm_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, doubl
         }
         a.flops = 2.0 * inside * double(a.k);
     }
+    // default: the persistent TMA kernel (gemm_f64_tma.cu); the cp.async kernel below serves
+    // operands TMA cannot address (odd leading dimension / 8-byte-aligned base) and cfg 1 / 2
+    if (g_dgemm_config == 0 || g_dgemm_config == 3) {
+        if (dgemm_tma_device(mode, ta, tb, m, n, a.k, alpha, A, lda, B, ldb, beta, C, ldc, gi0, gis, gj0, gjs,
+                             a.flops, s)) {
+            g_dgemm_last_kernel = 2;
+            return;
+        }
+    }
+    g_dgemm_last_kernel = 1;
     // A 'T' is K-major; B 'N' is K-major
     const bool ak = ta, bk = !tb;
     if (mode == 0) dispatch<0>(ak, bk, a, s);
@@ -388,6 +405,7 @@ void dgemm_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, doubl
 extern "C" {
 
 void elb200_dgemm_set_config(int cfg) { elb200::g_dgemm_config = cfg; }
+int elb200_dgemm_last_kernel(void) { return elb200::g_dgemm_last_kernel; }
 
 int elb200_dgemm(char transA, char transB, int64_t m, int64_t n, int64_t k, double alpha,
                  const double* A, int64_t lda, const double* B, int64_t ldb, double beta,

@@ -1,0 +1,443 @@
+// FP64 GEMM / TRRK, second generation: persistent, warp-specialised, TMA-fed DMMA kernel.
+//
+// Same contract as gemm_f64.cu (replaces blas::Gemm<double> -> dgemm_, reference
+// src/core/imports/blas/Gemm.hpp:431, and with MODE != 0 the LocalTrrk recursion of
+// src/blas_like/level3/Trrk/Local.hpp:782-830), built for the shape that dominates the
+// hot path: the rank-Blocksize() update C += A1 * B1 (k = 128..256) of SUMMA-C and of the
+// Cholesky trailing update, where the C read-modify-write and the pipeline fill of every
+// tile cost as much as the tile's DMMA work unless they are hidden.
+//
+// One CTA per SM, 12 warps (3 warpgroups):
+//   * two independent consumer groups of 4 warps; each group owns a stream of 128 x 64 C
+//     tiles (warp tile 64 x 32, accumulators in registers) and its own 4-stage operand ring,
+//     so while one group runs its epilogue the other keeps the FP64 tensor pipe busy
+//     (the DMMA pipe issues one m8n8k4 per 16 clocks per SM sub-partition: one resident
+//     warp per sub-partition saturates it);
+//   * a producer warpgroup that gives most of its registers to the consumers (setmaxnreg); two of
+//     its warps work (one per group): lane 0 issues the TMA loads
+//     (cp.async.bulk.tensor.2d, 128-byte swizzle, completion on an mbarrier) of every k-stage
+//     of every tile of its group and runs ahead across tile boundaries, so the pipeline never
+//     drains; all lanes prefetch the next C tile into L2 so the epilogue's loads are L2 hits.
+//
+// Shared-memory operand layouts (what TMA writes) and the conflict-free fragment reads:
+//   K-major operand (A 'T' / B 'N'; k contiguous in global memory): one box [rows][16 k],
+//     row pitch 128 B, 16-byte chunk index XORed with (row & 7).  An m8n8k4 fragment takes its
+//     8 rows in the order {0,2,4,6,1,3,5,7}: each half-warp (4 rows x 4 k) then touches 8
+//     distinct chunks x 2 halves = all 32 banks exactly once.
+//   MN-major operand (A 'N' / B 'T'; rows contiguous): boxes [16 k][16 rows], pitch 128 B,
+//     chunk XORed with (k & 7).  A fragment takes rows {0,1,8,9,2,3,10,11} (+4 for the second
+//     fragment of the box): again 16 distinct bank pairs per half-warp.
+//   The row permutations are undone in the epilogue (they only relabel rows/columns of C).
+// TMA zero-fills out-of-range rows / k, so ragged sizes need no special casing in the main
+// loop; the epilogue masks (and applies the global staircase mask for TRRK).
+//
+// Requirements: A, B 16-byte aligned with even leading dimension (TMA strides are multiples
+// of 16 B).  Anything else is served by the cp.async kernel of gemm_f64.cu.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "../common.hpp"
+#include "elb200_blas.h"
+
+namespace elb200 {
+namespace {
+
+constexpr int BK = 16;             // doubles per k-stage = one 128-byte swizzle span
+constexpr int TM = 128, TN = 64;   // C tile of one consumer group
+constexpr int STAGES = 4;
+constexpr int GROUPS = 2;
+constexpr int CONSUMER_WARPS = 4;  // per group
+// warpgroup 0 / 1: the consumer groups; warpgroup 2: producers (warps 8, 9 work, 10, 11 idle) --
+// three full warpgroups so that setmaxnreg can move registers from the producers to the consumers
+constexpr int NTHREADS = 32 * 4 * (GROUPS + 1);
+constexpr int CONSUMER_REGS = 232, PRODUCER_REGS = 40;  // 2*232 + 40 = 3*168: the launch-time budget
+constexpr int A_BYTES = TM * BK * 8;  // 16 KB
+constexpr int B_BYTES = TN * BK * 8;  //  8 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+constexpr int SMEM_BYTES = GROUPS * RING_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int GROUP_N = 16;  // tile columns per rasterisation band (in 64-column tiles)
+
+struct TmaArgs {
+    CUtensorMap mapA, mapB;
+    i64 m, n, k;
+    double* C;
+    i64 ldc;
+    double alpha, beta;
+    i64 gi0, gis, gj0, gjs;
+    i64 tilesM, tilesN;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ double lds64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ---- row permutations ---------------------------------------------------------------------
+// K-major operand: fragment f (8 rows) of a warp takes rows base + 8 f + PK[x], x = MMA row index
+__device__ __forceinline__ int permK(int x) { return ((x & 3) << 1) | (x >> 2); }
+// MN-major operand: fragment f takes rows base + 16 (f >> 1) + 4 (f & 1) + QM[x]
+__device__ __forceinline__ int permM(int x) { return ((x & 2) << 2) | (x & 1) | ((x & 4) >> 1); }  // {0,1,8,9,2,3,10,11}
+
+template <bool KMAJOR>
+__device__ __forceinline__ int tile_row(int f, int x) {
+    return KMAJOR ? (8 * f + permK(x)) : (16 * (f >> 1) + 4 * (f & 1) + permM(x));
+}
+
+// tile index -> (tm, tn): bands of GROUP_N tile columns, walked down the rows (L2 reuse of the
+// B band and of the A row panels across the CTAs that run concurrently)
+__device__ __forceinline__ void tile_coords(const TmaArgs& p, i64 tile, i64& tm, i64& tn) {
+    const i64 band_sz = (i64)GROUP_N * p.tilesM;
+    const i64 band = tile / band_sz;
+    const i64 first_n = band * GROUP_N;
+    const i64 bw = (p.tilesN - first_n < GROUP_N) ? (p.tilesN - first_n) : GROUP_N;
+    const i64 in_band = tile % band_sz;
+    tm = in_band / bw;
+    tn = first_n + in_band % bw;
+}
+
+template <int MODE>
+__device__ __forceinline__ bool tile_active(const TmaArgs& p, i64 tm, i64 tn) {
+    if (MODE == 0) return true;
+    const i64 m0 = tm * TM, n0 = tn * TN;
+    const i64 mlast = (m0 + TM - 1 < p.m - 1) ? (m0 + TM - 1) : (p.m - 1);
+    const i64 nlast = (n0 + TN - 1 < p.n - 1) ? (n0 + TN - 1) : (p.n - 1);
+    if (MODE == 1) return p.gi0 + mlast * p.gis >= p.gj0 + n0 * p.gjs;  // some gi >= gj
+    return p.gi0 + m0 * p.gis <= p.gj0 + nlast * p.gjs;                // some gi <= gj
+}
+
+// MODE 0: full GEMM; 1: lower-triangle TRRK; 2: upper-triangle TRRK
+template <bool A_KMAJOR, bool B_KMAJOR, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_tma_kernel(const __grid_constant__ TmaArgs p) {
+    extern __shared__ unsigned char smem_raw[];
+    const unsigned raw = smem_u32(smem_raw);
+    const unsigned base = (raw + 1023u) & ~1023u;       // 1024-byte alignment for the 128 B swizzle
+    const unsigned bars = base + GROUPS * RING_BYTES;   // full[G][S], empty[G][S]
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    // warps 0..7: consumers (group = warp / 4); warps 8, 9: producers of group 0, 1
+    const bool is_producer = warp >= GROUPS * CONSUMER_WARPS;
+    const int group = is_producer ? (warp - GROUPS * CONSUMER_WARPS) : (warp / CONSUMER_WARPS);
+    const unsigned ring = base + group * RING_BYTES;
+    const unsigned full0 = bars + (group * 2 * STAGES) * 8;
+    const unsigned empty0 = full0 + STAGES * 8;
+
+    if (tid == 0) {
+        for (int g2 = 0; g2 < GROUPS; ++g2)
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(bars + ((g2 * 2 * STAGES) + s) * 8, 1);
+                mbar_init(bars + ((g2 * 2 * STAGES) + STAGES + s) * 8, CONSUMER_WARPS);
+            }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
+
+    const i64 KT = (p.k + BK - 1) / BK;
+    const i64 total_tiles = p.tilesM * p.tilesN;
+    const i64 first_tile = (i64)blockIdx.x * GROUPS + group;
+    const i64 tile_step = (i64)gridDim.x * GROUPS;
+    const bool useC = (p.beta != 0.0);
+
+    if (is_producer) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
+        if (group >= GROUPS) return;  // idle warps of the producer warpgroup
+        // ================= producer warp: TMA loads + L2 prefetch of C =================
+        int stage = 0;
+        unsigned phase = 0;
+        for (i64 tile = first_tile; tile < total_tiles; tile += tile_step) {
+            i64 tm, tn;
+            tile_coords(p, tile, tm, tn);
+            if (!tile_active<MODE>(p, tm, tn)) continue;
+            const i64 m0 = tm * TM, n0 = tn * TN;
+            if (useC) {
+                // 64 columns x 128 rows x 8 B: lane handles columns lane and lane + 32
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const i64 col = n0 + lane + 32 * cc;
+                    if (col < p.n) {
+                        const char* cp = (const char*)(p.C + m0 + col * p.ldc);
+                        const i64 rows = (p.m - m0 < TM) ? (p.m - m0) : TM;
+                        const char* end = cp + rows * 8;
+                        for (const char* q = (const char*)((uintptr_t)cp & ~(uintptr_t)127); q < end; q += 128)
+                            prefetch_l2(q);
+                    }
+                }
+            }
+            for (i64 kt = 0; kt < KT; ++kt) {
+                mbar_wait(empty0 + stage * 8, phase ^ 1u);
+                if (lane == 0) {
+                    const unsigned full = full0 + stage * 8;
+                    const unsigned sa = ring + stage * STAGE_BYTES;
+                    const unsigned sb = sa + A_BYTES;
+                    mbar_expect_tx(full, STAGE_BYTES);
+                    const int k0 = (int)(kt * BK);
+                    if (A_KMAJOR) {
+                        tma_load_2d(sa, &p.mapA, k0, (int)m0, full);
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < TM / 16; ++b) tma_load_2d(sa + b * 2048, &p.mapA, (int)m0 + 16 * b, k0, full);
+                    }
+                    if (B_KMAJOR) {
+                        tma_load_2d(sb, &p.mapB, k0, (int)n0, full);
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < TN / 16; ++b) tma_load_2d(sb + b * 2048, &p.mapB, (int)n0 + 16 * b, k0, full);
+                    }
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+        return;
+    }
+
+    // ================= consumer warps =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
+    const int cw = warp % CONSUMER_WARPS;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (cw & 1) * 64, wn0 = (cw >> 1) * 32;
+
+    // per-lane fragment address pieces (bytes, relative to the operand's stage base)
+    //   K-major : row*128 + (((2ks + t/2) ^ (row&7)) << 4) + (t&1)*8,  row = wbase + 8f + PK[g]
+    //   MN-major: box*2048 + (4ks+t)*128 + (((rho/2) ^ ((4ks+t)&7)) << 4) + (rho&1)*8,
+    //             rho = 4(f&1) + QM[g], box = wbase/16 + f/2
+    unsigned aoff[4], boff[4];
+    if (A_KMAJOR) {
+        const int pr = permK(g);
+        const unsigned rowoff = (unsigned)(wm0 + pr) * 128u + (unsigned)(t & 1) * 8u;
+        const int L = pr ^ (t >> 1);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) aoff[ks] = rowoff + (unsigned)((L ^ (2 * ks)) << 4);
+    } else {
+        const int q = permM(g);
+        const unsigned lo = (unsigned)(wm0 / 16) * 2048u + (unsigned)t * 128u + (unsigned)(q & 1) * 8u;
+        const int L = (q >> 1) ^ t;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) aoff[x] = lo + (unsigned)((L ^ (2 * x)) << 4);  // x = (f&1) + 2*(ks&1)
+    }
+    if (B_KMAJOR) {
+        const int pr = permK(g);
+        const unsigned rowoff = (unsigned)(wn0 + pr) * 128u + (unsigned)(t & 1) * 8u;
+        const int L = pr ^ (t >> 1);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) boff[ks] = rowoff + (unsigned)((L ^ (2 * ks)) << 4);
+    } else {
+        const int q = permM(g);
+        const unsigned lo = (unsigned)(wn0 / 16) * 2048u + (unsigned)t * 128u + (unsigned)(q & 1) * 8u;
+        const int L = (q >> 1) ^ t;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) boff[x] = lo + (unsigned)((L ^ (2 * x)) << 4);
+    }
+
+    int stage = 0;
+    unsigned phase = 0;
+    const double alpha = p.alpha, beta = p.beta;
+
+    for (i64 tile = first_tile; tile < total_tiles; tile += tile_step) {
+        i64 tm, tn;
+        tile_coords(p, tile, tm, tn);
+        if (!tile_active<MODE>(p, tm, tn)) continue;
+        const i64 m0 = tm * TM, n0 = tn * TN;
+
+        double acc[8][4][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        for (i64 kt = 0; kt < KT; ++kt) {
+            mbar_wait(full0 + stage * 8, phase);
+            const unsigned sa = ring + stage * STAGE_BYTES;
+            const unsigned sb = sa + A_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < BK / 4; ++ks) {
+                double a[8], b[4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (A_KMAJOR) a[i] = lds64(sa + aoff[ks] + (unsigned)i * 1024u);
+                    else a[i] = lds64(sa + aoff[(i & 1) + 2 * (ks & 1)] + (unsigned)(i >> 1) * 2048u + (unsigned)ks * 512u);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (B_KMAJOR) b[j] = lds64(sb + boff[ks] + (unsigned)j * 1024u);
+                    else b[j] = lds64(sb + boff[(j & 1) + 2 * (ks & 1)] + (unsigned)(j >> 1) * 2048u + (unsigned)ks * 512u);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + stage * 8);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+
+        // ---- epilogue: C = alpha*acc + beta*C, masked; C was prefetched into L2 by the producer ----
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double old[2][8];
+            bool ok[2][8];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const i64 col = n0 + wn0 + tile_row<B_KMAJOR>(j, 2 * t + e);
+                const i64 gj = p.gj0 + col * p.gjs;
+                const double* cptr = p.C + col * p.ldc;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const i64 row = m0 + wm0 + tile_row<A_KMAJOR>(i, g);
+                    bool v = (col < p.n) && (row < p.m);
+                    if (MODE == 1) v = v && (p.gi0 + row * p.gis >= gj);
+                    if (MODE == 2) v = v && (p.gi0 + row * p.gis <= gj);
+                    ok[e][i] = v;
+                    old[e][i] = (v && useC) ? __ldcg(cptr + row) : 0.0;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const i64 col = n0 + wn0 + tile_row<B_KMAJOR>(j, 2 * t + e);
+                double* cptr = p.C + col * p.ldc;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const i64 row = m0 + wm0 + tile_row<A_KMAJOR>(i, g);
+                    if (ok[e][i]) {
+                        double v = alpha * acc[i][j][e];
+                        if (useC) v += beta * old[e][i];
+                        cptr[row] = v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    });
+    return fn;
+}
+
+// 2-D f64 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, outer stride ld
+void make_map(CUtensorMap* map, const double* ptr, i64 inner, i64 outer, i64 ld, int boxInner, int boxOuter) {
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 8u};
+    cuuint32_t box[2] = {(cuuint32_t)boxInner, (cuuint32_t)boxOuter};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)ptr, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+}
+
+template <bool AK, bool BKM, int MODE>
+void launch(const TmaArgs& a, double flops, cudaStream_t s) {
+    static bool configured = false;
+    auto kern = gemm_f64_tma_kernel<AK, BKM, MODE>;
+    if (!configured) {
+        ELB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const i64 tiles = a.tilesM * a.tilesN;
+    i64 grid = (tiles + GROUPS - 1) / GROUPS;
+    if (grid > sm_count()) grid = sm_count();
+    gemm_profile_begin(s);
+    kern<<<(unsigned)grid, NTHREADS, SMEM_BYTES, s>>>(a);
+    ELB_LAUNCH_CHECK();
+    gemm_profile_end(s, flops);
+}
+
+template <int MODE>
+void dispatch(bool ak, bool bk, const TmaArgs& a, double flops, cudaStream_t s) {
+    if (ak) {
+        if (bk) launch<true, true, MODE>(a, flops, s);
+        else launch<true, false, MODE>(a, flops, s);
+    } else {
+        if (bk) launch<false, true, MODE>(a, flops, s);
+        else launch<false, false, MODE>(a, flops, s);
+    }
+}
+
+}  // namespace
+
+// Returns false (nothing launched) when the operands do not meet TMA's alignment rules.
+// ta / tb: op(A) / op(B) is the transpose of the stored matrix.
+bool dgemm_tma_device(int mode, bool ta, bool tb, i64 m, i64 n, i64 k, double alpha, const double* A, i64 lda,
+                      const double* B, i64 ldb, double beta, double* C, i64 ldc, i64 gi0, i64 gis, i64 gj0, i64 gjs,
+                      double flops, cudaStream_t s) {
+    if (k <= 0 || m <= 0 || n <= 0) return false;
+    if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda & 1) || (ldb & 1)) return false;
+    if (m >= (i64(1) << 31) || n >= (i64(1) << 31) || k >= (i64(1) << 31)) return false;
+    if (!encode_fn()) return false;
+    TmaArgs a;
+    // A 'T' is K-major: stored k x m, k contiguous.  A 'N' is MN-major: stored m x k, m contiguous.
+    const bool ak = ta, bk = !tb;
+    if (ak) make_map(&a.mapA, A, k, m, lda, BK, TM);
+    else make_map(&a.mapA, A, m, k, lda, 16, BK);
+    if (bk) make_map(&a.mapB, B, k, n, ldb, BK, TN);
+    else make_map(&a.mapB, B, n, k, ldb, 16, BK);
+    a.m = m; a.n = n; a.k = k;
+    a.C = C; a.ldc = ldc;
+    a.alpha = alpha; a.beta = beta;
+    a.gi0 = gi0; a.gis = gis; a.gj0 = gj0; a.gjs = gjs;
+    a.tilesM = ceil_div(m, TM);
+    a.tilesN = ceil_div(n, TN);
+    if (mode == 0) dispatch<0>(ak, bk, a, flops, s);
+    else if (mode == 1) dispatch<1>(ak, bk, a, flops, s);
+    else dispatch<2>(ak, bk, a, flops, s);
+    return true;
+}
+
+}  // namespace elb200

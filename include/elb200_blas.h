@@ -53,9 +53,13 @@ unsigned long long elb200_launch_count(int reset);
 void elb200_gemm_profile(int enable);
 int elb200_gemm_profile_read(double* total_ms, long long* launches, double* flops);
 
-/* FP64 GEMM tile configuration: 0 automatic (default), 1 = 128x128 CTA tile, one CTA per SM,
- * 2 = 128x64 CTA tile, two CTAs per SM (epilogue of one overlaps the main loop of the other) */
+/* FP64 GEMM kernel selection: 0 automatic (default: the persistent warp-specialised TMA kernel
+ * whenever A and B are 16-byte aligned with even leading dimension, else the cp.async kernel),
+ * 1 = cp.async kernel, 128x128 CTA tile, one CTA per SM, 2 = cp.async kernel, 128x64 CTA tile,
+ * two CTAs per SM, 3 = same as 0 */
 void elb200_dgemm_set_config(int cfg);
+/* which kernel the last elb200_dgemm / dtrrk / dsyrk call launched: 1 cp.async, 2 TMA */
+int elb200_dgemm_last_kernel(void);
 
 /* ---- GEMM: C := alpha op(A) op(B) + beta C ---------------------------- */
 /* trans in {'N','T','C'}; for real types 'C' == 'T' (blas/Gemm.hpp:386-387) */

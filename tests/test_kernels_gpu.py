@@ -159,3 +159,83 @@ def test_fortran_abi_dgemm_on_current_stream():
              dC.ptr, i(dC.ld))
     torch.cuda.synchronize()
     assert np.linalg.norm(dC.get() - (3 * A @ B + 4 * C0)) <= 1e-12 * k
+
+
+def _even(x):
+    return x + (x & 1)
+
+
+def test_dgemm_tma_kernel_all_orientations_ragged():
+    """The persistent TMA kernel (16-byte aligned operands, even ld): every orientation, ragged
+    sizes around the 128x64 tile and the 16-deep k-stage, many tiles per CTA (persistence), k
+    long enough to wrap the 4-stage ring several times."""
+    import gpuutil as G
+    from elemental_b200._lib import lib
+    L = lib()
+    rng = np.random.default_rng(7)
+    dt = np.float64
+    shapes = [(128, 64, 16), (1, 1, 1), (7, 5, 3), (130, 257, 45), (257, 129, 200), (64, 300, 0), (1000, 900, 333),
+              (384, 2112, 130), (4100, 3100, 70)]
+    for (m, n, k) in shapes:
+        for ta in "NT":
+            for tb in "NT":
+                A = G.rand(rng, *((m, k) if ta == "N" else (k, m)), dt)
+                B = G.rand(rng, *((k, n) if tb == "N" else (n, k)), dt)
+                C0 = G.rand(rng, m, n, dt)
+                dA = G.DevMat(A, _even(A.shape[0] + 2)); dB = G.DevMat(B, _even(B.shape[0] + 4), offset=2)
+                dC = G.DevMat(C0, m + 5, offset=1)
+                for alpha, beta in ((3.0, 4.0), (1.0, 0.0)):
+                    dC.t.copy_(__import__("torch").from_numpy(dC.host0))
+                    G.gemm(ta, tb, alpha, dA, dB, beta, dC, k)
+                    if k > 0:
+                        assert L.elb200_dgemm_last_kernel() == 2, "TMA kernel was not selected"
+                    ref = alpha * (_op(A, ta) @ _op(B, tb)) + beta * C0 if k else beta * C0
+                    got = dC.get()
+                    tol = 4 * max(k, 1) * G.eps(dt) * max(np.linalg.norm(A) * np.linalg.norm(B), 1) + 8 * G.eps(dt) * np.linalg.norm(C0) * abs(beta)
+                    assert np.linalg.norm(got - ref) <= tol, (ta, tb, m, n, k, alpha, beta)
+                    assert dC.padding_untouched()
+
+
+def test_dtrrk_tma_kernel_staircase():
+    import gpuutil as G
+    from elemental_b200._lib import lib
+    L = lib()
+    rng = np.random.default_rng(8)
+    dt = np.float64
+    for (m, n, k, rs, rst, cs, cst) in [(300, 300, 40, 0, 1, 0, 1), (257, 131, 33, 1, 2, 3, 4), (131, 257, 64, 0, 2, 1, 4),
+                                       (1029, 517, 256, 1, 2, 0, 4), (700, 700, 128, 0, 1, 0, 1)]:
+        for uplo in "LU":
+            for ta, tb in (("T", "N"), ("N", "T"), ("N", "N"), ("T", "T")):
+                A = G.rand(rng, *((m, k) if ta == "N" else (k, m)), dt)
+                B = G.rand(rng, *((k, n) if tb == "N" else (n, k)), dt)
+                C0 = G.rand(rng, m, n, dt)
+                dA, dB, dC = G.DevMat(A, _even(A.shape[0])), G.DevMat(B, _even(B.shape[0] + 2)), G.DevMat(C0, m + 3)
+                G.trrk(uplo, ta, tb, -1.0, dA, dB, 1.0, dC, k, rs, rst, cs, cst)
+                assert L.elb200_dgemm_last_kernel() == 2
+                full = -(_op(A, ta) @ _op(B, tb)) + C0
+                gi = rs + rst * np.arange(m)[:, None]; gj = cs + cst * np.arange(n)[None, :]
+                mask = gi >= gj if uplo == "L" else gi <= gj
+                got = dC.get()
+                assert np.array_equal(got[~mask], C0[~mask])
+                tol = 4 * k * G.eps(dt) * np.linalg.norm(A) * np.linalg.norm(B)
+                assert np.linalg.norm((got - full)[mask]) <= tol
+                assert dC.padding_untouched()
+
+
+def test_dgemm_kernels_agree_bitwise_free_of_order():
+    """cp.async and TMA kernels accumulate each C entry over k in the same order (k ascending in
+    steps of 4 inside one accumulator), so they must agree to the last bit."""
+    import gpuutil as G
+    from elemental_b200._lib import lib
+    L = lib()
+    rng = np.random.default_rng(9)
+    m, n, k = 515, 390, 777
+    A = G.rand(rng, m, k, np.float64); B = G.rand(rng, k, n, np.float64); C0 = G.rand(rng, m, n, np.float64)
+    outs = []
+    for cfg in (2, 3):
+        L.elb200_dgemm_set_config(cfg)
+        dA, dB, dC = G.DevMat(A, _even(m)), G.DevMat(B, _even(k)), G.DevMat(C0, m)
+        G.gemm("N", "N", 1.5, dA, dB, -0.5, dC, k)
+        outs.append(dC.get())
+    L.elb200_dgemm_set_config(0)
+    assert np.array_equal(outs[0], outs[1])
