@@ -7,17 +7,17 @@
 // Cholesky trailing update, where the C read-modify-write and the pipeline fill of every
 // tile cost as much as the tile's DMMA work unless they are hidden.
 //
-// One CTA per SM, 12 warps (3 warpgroups):
-//   * two independent consumer groups of 4 warps; each group owns a stream of 128 x 64 C
-//     tiles (warp tile 64 x 32, accumulators in registers) and its own 4-stage operand ring,
-//     so while one group runs its epilogue the other keeps the FP64 tensor pipe busy
-//     (the DMMA pipe issues one m8n8k4 per 16 clocks per SM sub-partition: one resident
-//     warp per sub-partition saturates it);
-//   * a producer warpgroup that gives most of its registers to the consumers (setmaxnreg); two of
-//     its warps work (one per group): lane 0 issues the TMA loads
-//     (cp.async.bulk.tensor.2d, 128-byte swizzle, completion on an mbarrier) of every k-stage
-//     of every tile of its group and runs ahead across tile boundaries, so the pipeline never
-//     drains; all lanes prefetch the next C tile into L2 so the epilogue's loads are L2 hits.
+// One persistent CTA per SM, 8 warps:
+//   * two independent groups of 4 warps; each group owns a stream of 128 x 64 C tiles (warp
+//     tile 64 x 32, accumulators in registers) and its own 4-stage operand ring, so while one
+//     group runs its epilogue the other keeps the FP64 tensor pipe busy (the DMMA pipe issues
+//     one m8n8k4 per 16 clocks per SM sub-partition; two resident warps per sub-partition hide
+//     each other's fixed issue latencies);
+//   * warp 0 of each group also carries the group's producer cursor: before consuming k-stage i
+//     its lane 0 issues the TMA loads (cp.async.bulk.tensor.2d, 128-byte swizzle, completion on
+//     an mbarrier) of k-stage i+2 -- across tile boundaries, so the pipeline never drains -- and
+//     when the cursor enters a new tile all its lanes prefetch that C tile into L2, which makes
+//     the epilogue's read-modify-write loads L2 hits.
 //
 // Shared-memory operand layouts (what TMA writes) and the conflict-free fragment reads:
 //   K-major operand (A 'T' / B 'N'; k contiguous in global memory): one box [rows][16 k],
@@ -41,6 +41,7 @@
 #include "elb200_blas.h"
 
 namespace elb200 {
+int g_dgemm_tma_flags = 0;
 namespace {
 
 constexpr int BK = 16;             // doubles per k-stage = one 128-byte swizzle span
@@ -48,15 +49,19 @@ constexpr int TM = 128, TN = 64;   // C tile of one consumer group
 constexpr int STAGES = 4;
 constexpr int GROUPS = 2;
 constexpr int CONSUMER_WARPS = 4;  // per group
-// warpgroup 0 / 1: the consumer groups; warpgroup 2: producers (warps 8, 9 work, 10, 11 idle) --
-// three full warpgroups so that setmaxnreg can move registers from the producers to the consumers
-constexpr int NTHREADS = 32 * 4 * (GROUPS + 1);
-constexpr int CONSUMER_REGS = 232, PRODUCER_REGS = 40;  // 2*232 + 40 = 3*168: the launch-time budget
+// 8 warps = 2 per SM sub-partition, so every thread may use up to 255 registers (128 of them hold
+// the 64 x 32 warp tile).  A dedicated producer warpgroup with setmaxnreg (168 -> 40 / 232) was
+// measured too: upper registers obtained that way were intermittently corrupted while global loads
+// into them were in flight (wrong C read-modify-write), so the TMA issue lives in
+// warp 0 of each group instead.
+constexpr int NTHREADS = 32 * GROUPS * CONSUMER_WARPS;
+constexpr int LOOKAHEAD = 2;  // k-stages the producer cursor runs ahead (<= STAGES - 2: no lock-step)
 constexpr int A_BYTES = TM * BK * 8;  // 16 KB
 constexpr int B_BYTES = TN * BK * 8;  //  8 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int RING_BYTES = STAGES * STAGE_BYTES;
 constexpr int SMEM_BYTES = GROUPS * RING_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int GO_BAR_OFFSET = GROUPS * 2 * STAGES * 8;  // the stagger barrier follows full/empty[G][S]
 constexpr int GROUP_N = 16;  // tile columns per rasterisation band (in 64-column tiles)
 
 struct TmaArgs {
@@ -67,6 +72,7 @@ struct TmaArgs {
     double alpha, beta;
     i64 gi0, gis, gj0, gjs;
     i64 tilesM, tilesN;
+    int flags;  // tuning/debug: bit0 = stagger the two groups, bit1 = always use the masked epilogue
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -146,19 +152,38 @@ __device__ __forceinline__ bool tile_active(const TmaArgs& p, i64 tm, i64 tn) {
     return p.gi0 + m0 * p.gis <= p.gj0 + nlast * p.gjs;                // some gi <= gj
 }
 
+// One k-stage of loads for the tile at (m0, n0): expect_tx + TMA boxes, issued by one lane
+template <bool A_KMAJOR, bool B_KMAJOR>
+__device__ __forceinline__ void issue_stage(const TmaArgs& p, unsigned sa, unsigned full, i64 m0, i64 n0, i64 kt) {
+    const unsigned sb = sa + A_BYTES;
+    mbar_expect_tx(full, STAGE_BYTES);
+    const int k0 = (int)(kt * BK);
+    if (A_KMAJOR) {
+        tma_load_2d(sa, &p.mapA, k0, (int)m0, full);
+    } else {
+#pragma unroll
+        for (int b = 0; b < TM / 16; ++b) tma_load_2d(sa + b * 2048, &p.mapA, (int)m0 + 16 * b, k0, full);
+    }
+    if (B_KMAJOR) {
+        tma_load_2d(sb, &p.mapB, k0, (int)n0, full);
+    } else {
+#pragma unroll
+        for (int b = 0; b < TN / 16; ++b) tma_load_2d(sb + b * 2048, &p.mapB, (int)n0 + 16 * b, k0, full);
+    }
+}
+
 // MODE 0: full GEMM; 1: lower-triangle TRRK; 2: upper-triangle TRRK
 template <bool A_KMAJOR, bool B_KMAJOR, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_tma_kernel(const __grid_constant__ TmaArgs p) {
     extern __shared__ unsigned char smem_raw[];
     const unsigned raw = smem_u32(smem_raw);
     const unsigned base = (raw + 1023u) & ~1023u;       // 1024-byte alignment for the 128 B swizzle
-    const unsigned bars = base + GROUPS * RING_BYTES;   // full[G][S], empty[G][S]
+    const unsigned bars = base + GROUPS * RING_BYTES;   // full[G][S], empty[G][S], go
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    // warps 0..7: consumers (group = warp / 4); warps 8, 9: producers of group 0, 1
-    const bool is_producer = warp >= GROUPS * CONSUMER_WARPS;
-    const int group = is_producer ? (warp - GROUPS * CONSUMER_WARPS) : (warp / CONSUMER_WARPS);
+    const int group = warp / CONSUMER_WARPS;
+    const int cw = warp % CONSUMER_WARPS;
     const unsigned ring = base + group * RING_BYTES;
     const unsigned full0 = bars + (group * 2 * STAGES) * 8;
     const unsigned empty0 = full0 + STAGES * 8;
@@ -169,6 +194,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_tma_kernel(const __grid_
                 mbar_init(bars + ((g2 * 2 * STAGES) + s) * 8, 1);
                 mbar_init(bars + ((g2 * 2 * STAGES) + STAGES + s) * 8, CONSUMER_WARPS);
             }
+        mbar_init(bars + GO_BAR_OFFSET, CONSUMER_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async;" ::: "memory");
     }
@@ -180,62 +206,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_tma_kernel(const __grid_
     const i64 tile_step = (i64)gridDim.x * GROUPS;
     const bool useC = (p.beta != 0.0);
 
-    if (is_producer) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
-        if (group >= GROUPS) return;  // idle warps of the producer warpgroup
-        // ================= producer warp: TMA loads + L2 prefetch of C =================
-        int stage = 0;
-        unsigned phase = 0;
-        for (i64 tile = first_tile; tile < total_tiles; tile += tile_step) {
-            i64 tm, tn;
-            tile_coords(p, tile, tm, tn);
-            if (!tile_active<MODE>(p, tm, tn)) continue;
-            const i64 m0 = tm * TM, n0 = tn * TN;
-            if (useC) {
-                // 64 columns x 128 rows x 8 B: lane handles columns lane and lane + 32
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const i64 col = n0 + lane + 32 * cc;
-                    if (col < p.n) {
-                        const char* cp = (const char*)(p.C + m0 + col * p.ldc);
-                        const i64 rows = (p.m - m0 < TM) ? (p.m - m0) : TM;
-                        const char* end = cp + rows * 8;
-                        for (const char* q = (const char*)((uintptr_t)cp & ~(uintptr_t)127); q < end; q += 128)
-                            prefetch_l2(q);
-                    }
-                }
-            }
-            for (i64 kt = 0; kt < KT; ++kt) {
-                mbar_wait(empty0 + stage * 8, phase ^ 1u);
-                if (lane == 0) {
-                    const unsigned full = full0 + stage * 8;
-                    const unsigned sa = ring + stage * STAGE_BYTES;
-                    const unsigned sb = sa + A_BYTES;
-                    mbar_expect_tx(full, STAGE_BYTES);
-                    const int k0 = (int)(kt * BK);
-                    if (A_KMAJOR) {
-                        tma_load_2d(sa, &p.mapA, k0, (int)m0, full);
-                    } else {
-#pragma unroll
-                        for (int b = 0; b < TM / 16; ++b) tma_load_2d(sa + b * 2048, &p.mapA, (int)m0 + 16 * b, k0, full);
-                    }
-                    if (B_KMAJOR) {
-                        tma_load_2d(sb, &p.mapB, k0, (int)n0, full);
-                    } else {
-#pragma unroll
-                        for (int b = 0; b < TN / 16; ++b) tma_load_2d(sb + b * 2048, &p.mapB, (int)n0 + 16 * b, k0, full);
-                    }
-                }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-            }
-        }
-        return;
-    }
-
-    // ================= consumer warps =================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
-    const int cw = warp % CONSUMER_WARPS;
     const int g = lane >> 2, t = lane & 3;
     const int wm0 = (cw & 1) * 64, wn0 = (cw >> 1) * 32;
 
@@ -271,9 +241,60 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_tma_kernel(const __grid_
         for (int x = 0; x < 4; ++x) boff[x] = lo + (unsigned)((L ^ (2 * x)) << 4);
     }
 
+    // ---- producer cursor (warp 0 of the group): runs LOOKAHEAD k-stages ahead of the consumers,
+    //      across tile boundaries ----
+    i64 ptile = first_tile, pkt = 0, pm0 = 0, pn0 = 0;
+    int pstage = 0;
+    unsigned pphase = 0;
+    bool pvalid = false;
+    // move the producer cursor to the next active tile at or after `from`; prefetch its C tile into L2
+    auto producer_seek = [&](i64 from) {
+        pvalid = false;
+        for (i64 tile = from; tile < total_tiles; tile += tile_step) {
+            i64 tm, tn;
+            tile_coords(p, tile, tm, tn);
+            if (!tile_active<MODE>(p, tm, tn)) continue;
+            ptile = tile; pm0 = tm * TM; pn0 = tn * TN; pkt = 0; pvalid = true;
+            break;
+        }
+        if (pvalid && useC) {
+            // 64 columns x 128 rows x 8 B: lane handles columns lane and lane + 32
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const i64 col = pn0 + lane + 32 * cc;
+                if (col < p.n) {
+                    const char* cp = (const char*)(p.C + pm0 + col * p.ldc);
+                    const i64 rows = (p.m - pm0 < TM) ? (p.m - pm0) : TM;
+                    const char* end = cp + rows * 8;
+                    for (const char* q = (const char*)((uintptr_t)cp & ~(uintptr_t)127); q < end; q += 128) prefetch_l2(q);
+                }
+            }
+        }
+    };
+    // issue the loads of one k-stage at the producer cursor and advance it
+    auto producer_step = [&]() {
+        if (!pvalid) return;
+        mbar_wait(empty0 + pstage * 8, pphase ^ 1u);
+        if (lane == 0)
+            issue_stage<A_KMAJOR, B_KMAJOR>(p, ring + pstage * STAGE_BYTES, full0 + pstage * 8, pm0, pn0, pkt);
+        __syncwarp();
+        if (++pstage == STAGES) { pstage = 0; pphase ^= 1u; }
+        if (++pkt == KT) producer_seek(ptile + tile_step);
+    };
+    if (cw == 0) {
+        producer_seek(first_tile);
+#pragma unroll 1
+        for (int i = 0; i < LOOKAHEAD; ++i) producer_step();
+    }
+
     int stage = 0;
     unsigned phase = 0;
     const double alpha = p.alpha, beta = p.beta;
+    // Optional stagger (flags bit 0): group 1 starts its first tile when group 0 is half-way
+    // through its own, so that the epilogue of one group runs under the main loop of the other.
+    const unsigned go_bar = bars + GO_BAR_OFFSET;
+    const bool stagger = (p.flags & 1) != 0;
+    bool released = false;  // group 0: has signalled; group 1: has waited
 
     for (i64 tile = first_tile; tile < total_tiles; tile += tile_step) {
         i64 tm, tn;
@@ -287,7 +308,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_tma_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+        if (stagger && group == 1 && !released) {
+            mbar_wait(go_bar, 0);
+            released = true;
+        }
+#pragma unroll 1
         for (i64 kt = 0; kt < KT; ++kt) {
+            if (stagger && group == 0 && !released && 2 * kt + 1 >= KT) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(go_bar);
+                released = true;
+            }
+            if (cw == 0) producer_step();
             mbar_wait(full0 + stage * 8, phase);
             const unsigned sa = ring + stage * STAGE_BYTES;
             const unsigned sb = sa + A_BYTES;
@@ -314,41 +346,81 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_tma_kernel(const __grid_
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
 
-        // ---- epilogue: C = alpha*acc + beta*C, masked; C was prefetched into L2 by the producer ----
+        // ---- epilogue: C = alpha*acc + beta*C; C was prefetched into L2 by the producer ----
+        bool interior = (m0 + TM <= p.m) && (n0 + TN <= p.n);
+        if (MODE == 1) interior = interior && (p.gi0 + m0 * p.gis >= p.gj0 + (n0 + TN - 1) * p.gjs);
+        if (MODE == 2) interior = interior && (p.gi0 + (m0 + TM - 1) * p.gis <= p.gj0 + n0 * p.gjs);
+        if (interior && !(p.flags & 2)) {
+            // fast path (all but the edge / diagonal tiles): no masks, one base pointer per column
+            // and compile-time row offsets; two memory round trips per tile
+            double* cbase = p.C + (m0 + wm0 + tile_row<A_KMAJOR>(0, g)) + (n0 + wn0) * p.ldc;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            double old[2][8];
-            bool ok[2][8];
+            for (int jj = 0; jj < 4; jj += 2) {
+                double old[2][2][8];
+                if (useC) {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const i64 col = n0 + wn0 + tile_row<B_KMAJOR>(j, 2 * t + e);
-                const i64 gj = p.gj0 + col * p.gjs;
-                const double* cptr = p.C + col * p.ldc;
+                    for (int j2 = 0; j2 < 2; ++j2)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const i64 row = m0 + wm0 + tile_row<A_KMAJOR>(i, g);
-                    bool v = (col < p.n) && (row < p.m);
-                    if (MODE == 1) v = v && (p.gi0 + row * p.gis >= gj);
-                    if (MODE == 2) v = v && (p.gi0 + row * p.gis <= gj);
-                    ok[e][i] = v;
-                    old[e][i] = (v && useC) ? __ldcg(cptr + row) : 0.0;
+                        for (int e = 0; e < 2; ++e) {
+                            const double* cptr = cbase + (i64)tile_row<B_KMAJOR>(jj + j2, 2 * t + e) * p.ldc;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) old[j2][e][i] = __ldcg(cptr + tile_row<A_KMAJOR>(i, 0));
+                        }
                 }
+#pragma unroll
+                for (int j2 = 0; j2 < 2; ++j2)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        double* cptr = cbase + (i64)tile_row<B_KMAJOR>(jj + j2, 2 * t + e) * p.ldc;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            double v = alpha * acc[i][jj + j2][e];
+                            if (useC) v += beta * old[j2][e][i];
+                            cptr[tile_row<A_KMAJOR>(i, 0)] = v;
+                        }
+                    }
             }
+        } else {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const i64 col = n0 + wn0 + tile_row<B_KMAJOR>(j, 2 * t + e);
-                double* cptr = p.C + col * p.ldc;
+            for (int j = 0; j < 4; ++j) {
+                double old[2][8];
+                bool ok[2][8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const i64 row = m0 + wm0 + tile_row<A_KMAJOR>(i, g);
-                    if (ok[e][i]) {
-                        double v = alpha * acc[i][j][e];
-                        if (useC) v += beta * old[e][i];
-                        cptr[row] = v;
+                for (int e = 0; e < 2; ++e) {
+                    const i64 col = n0 + wn0 + tile_row<B_KMAJOR>(j, 2 * t + e);
+                    const i64 gj = p.gj0 + col * p.gjs;
+                    const double* cptr = p.C + col * p.ldc;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const i64 row = m0 + wm0 + tile_row<A_KMAJOR>(i, g);
+                        bool v = (col < p.n) && (row < p.m);
+                        if (MODE == 1) v = v && (p.gi0 + row * p.gis >= gj);
+                        if (MODE == 2) v = v && (p.gi0 + row * p.gis <= gj);
+                        ok[e][i] = v;
+                        old[e][i] = (v && useC) ? __ldcg(cptr + row) : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const i64 col = n0 + wn0 + tile_row<B_KMAJOR>(j, 2 * t + e);
+                    double* cptr = p.C + col * p.ldc;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const i64 row = m0 + wm0 + tile_row<A_KMAJOR>(i, g);
+                        if (ok[e][i]) {
+                            double v = alpha * acc[i][j][e];
+                            if (useC) v += beta * old[e][i];
+                            cptr[row] = v;
+                        }
                     }
                 }
             }
         }
+    }
+    // a group that never ran a tile must still release the other one
+    if (stagger && group == 0 && !released) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(go_bar);
     }
 }
 
@@ -434,6 +506,7 @@ bool dgemm_tma_device(int mode, bool ta, bool tb, i64 m, i64 n, i64 k, double al
     a.gi0 = gi0; a.gis = gis; a.gj0 = gj0; a.gjs = gjs;
     a.tilesM = ceil_div(m, TM);
     a.tilesN = ceil_div(n, TN);
+    a.flags = g_dgemm_tma_flags;
     if (mode == 0) dispatch<0>(ak, bk, a, flops, s);
     else if (mode == 1) dispatch<1>(ak, bk, a, flops, s);
     else dispatch<2>(ak, bk, a, flops, s);
@@ -441,3 +514,5 @@ bool dgemm_tma_device(int mode, bool ta, bool tb, i64 m, i64 n, i64 k, double al
 }
 
 }  // namespace elb200
+
+extern "C" void elb200_dgemm_set_debug_flags(int f) { elb200::g_dgemm_tma_flags = f; }
