@@ -286,8 +286,8 @@ __global__ void __launch_bounds__(CF::NT, CF::MINB) gemm_f64_kernel(const GemmAr
             for (int i = 0; i < 8; ++i) {
                 const i64 row = m0 + wm0 + i * 8 + g;
                 if (ok[e][i]) {
-                    double v = alpha * acc[i][j][e];
-                    if (useC) v += beta * old[e][i];
+                    double v = __dmul_rn(alpha, acc[i][j][e]);
+                    if (useC) v = __fma_rn(beta, old[e][i], v);
                     cptr[row] = v;
                 }
             }

@@ -48,14 +48,26 @@ constexpr int BK = 16;             // doubles per k-stage = one 128-byte swizzle
 constexpr int TM = 128, TN = 64;   // C tile of one consumer group
 constexpr int STAGES = 4;
 constexpr int GROUPS = 2;
-constexpr int CONSUMER_WARPS = 4;  // per group
+// Warp layout of one group.  A lone warp per SM sub-partition sustains only ~62 % of the DMMA issue
+// rate (measured: flags bit 2), two or more saturate it.  Cfg8 = 8 warps per group (warp tile
+// 32 x 32): even while the other group is in its epilogue the pipe still sees two warps per
+// sub-partition.  Cfg4 = 4 warps per group (warp tile 64 x 32): fewer shared-memory reads per DMMA.
+template <int WM_, int WN_>
+struct GroupCfg {
+    static constexpr int WM = WM_, WN = WN_;
+    static constexpr int WARPS = WM * WN;           // warps per group
+    static constexpr int FM = 128 / (8 * WM);       // 8-row A fragments per warp
+    static constexpr int FN = 64 / (8 * WN);        // 8-column B fragments per warp
+    static constexpr int NTHREADS = 32 * 2 * WARPS;
+};
+typedef GroupCfg<2, 2> Cfg4;
+typedef GroupCfg<4, 2> Cfg8;
 // 8 warps = 2 per SM sub-partition, so every thread may use up to 255 registers (128 of them hold
 // the 64 x 32 warp tile).  A dedicated producer warpgroup with setmaxnreg (168 -> 40 / 232) was
 // measured too: upper registers obtained that way were intermittently corrupted while global loads
 // into them were in flight (wrong C read-modify-write), so the TMA issue lives in
 // warp 0 of each group instead.
-constexpr int NTHREADS = 32 * GROUPS * CONSUMER_WARPS;
-constexpr int LOOKAHEAD = 2;  // k-stages the producer cursor runs ahead (<= STAGES - 2: no lock-step)
+constexpr int LOOKAHEAD = 3;  // k-stages the producer cursor runs ahead of the consumers (< STAGES)
 constexpr int A_BYTES = TM * BK * 8;  // 16 KB
 constexpr int B_BYTES = TN * BK * 8;  //  8 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -72,7 +84,9 @@ struct TmaArgs {
     double alpha, beta;
     i64 gi0, gis, gj0, gjs;
     i64 tilesM, tilesN;
-    int flags;  // tuning/debug: bit0 = stagger the two groups, bit1 = always use the masked epilogue
+    int flags;  // tuning/debug: bit0 = stagger the two groups, bit1 = always use the masked epilogue,
+                // bit2 = only group 0 works, bit3 = 4 warps per group (warp tile 64 x 32) instead of 8,
+                // bit4 = never use the L2 reduction epilogue
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -108,6 +122,13 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+// C[i] += v performed by the L2 atomic unit: no load, no register for the old value, nothing to wait
+// for.  Each C entry is touched by exactly one thread per launch, so the result is deterministic and
+// equal to the load-add-store form.  Measured 2.4 TB/s of C bytes with the epilogue's access pattern
+// (scripts/micro/bulk_red_f64.cu), i.e. HBM-bound like a plain read-modify-write stream.
+__device__ __forceinline__ void red_add_f64(double* addr, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
 __device__ __forceinline__ double lds64(unsigned addr) {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -131,15 +152,19 @@ __device__ __forceinline__ int tile_row(int f, int x) {
 }
 
 // tile index -> (tm, tn): bands of GROUP_N tile columns, walked down the rows (L2 reuse of the
-// B band and of the A row panels across the CTAs that run concurrently)
-__device__ __forceinline__ void tile_coords(const TmaArgs& p, i64 tile, i64& tm, i64& tn) {
-    const i64 band_sz = (i64)GROUP_N * p.tilesM;
-    const i64 band = tile / band_sz;
-    const i64 first_n = band * GROUP_N;
-    const i64 bw = (p.tilesN - first_n < GROUP_N) ? (p.tilesN - first_n) : GROUP_N;
-    const i64 in_band = tile % band_sz;
-    tm = in_band / bw;
-    tn = first_n + in_band % bw;
+// B band and of the A row panels across the CTAs that run concurrently).  32-bit arithmetic: the
+// host guarantees tilesM * tilesN < 2^31.
+__device__ __forceinline__ void tile_coords(const TmaArgs& p, i64 tile64, i64& tm, i64& tn) {
+    const unsigned tile = (unsigned)tile64;
+    const unsigned tilesM = (unsigned)p.tilesM, tilesN = (unsigned)p.tilesN;
+    const unsigned band_sz = (unsigned)GROUP_N * tilesM;
+    const unsigned band = tile / band_sz;
+    const unsigned first_n = band * GROUP_N;
+    const unsigned bw = (tilesN - first_n < (unsigned)GROUP_N) ? (tilesN - first_n) : (unsigned)GROUP_N;
+    const unsigned in_band = tile - band * band_sz;
+    const unsigned q = in_band / bw;
+    tm = q;
+    tn = first_n + (in_band - q * bw);
 }
 
 template <int MODE>
@@ -173,8 +198,9 @@ __device__ __forceinline__ void issue_stage(const TmaArgs& p, unsigned sa, unsig
 }
 
 // MODE 0: full GEMM; 1: lower-triangle TRRK; 2: upper-triangle TRRK
-template <bool A_KMAJOR, bool B_KMAJOR, int MODE>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_tma_kernel(const __grid_constant__ TmaArgs p) {
+template <class CF, bool A_KMAJOR, bool B_KMAJOR, int MODE>
+__global__ void __launch_bounds__(CF::NTHREADS, 1) gemm_f64_tma_kernel(const __grid_constant__ TmaArgs p) {
+    constexpr int CONSUMER_WARPS = CF::WARPS, FM = CF::FM, FN = CF::FN;
     extern __shared__ unsigned char smem_raw[];
     const unsigned raw = smem_u32(smem_raw);
     const unsigned base = (raw + 1023u) & ~1023u;       // 1024-byte alignment for the 128 B swizzle
@@ -202,12 +228,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_tma_kernel(const __grid_
 
     const i64 KT = (p.k + BK - 1) / BK;
     const i64 total_tiles = p.tilesM * p.tilesN;
-    const i64 first_tile = (i64)blockIdx.x * GROUPS + group;
-    const i64 tile_step = (i64)gridDim.x * GROUPS;
+    const bool single = (p.flags & 4) != 0;  // experiment: only group 0 works (lone-warp DMMA rate)
+    if (single && group == 1) return;
+    const i64 first_tile = single ? (i64)blockIdx.x : (i64)blockIdx.x * GROUPS + group;
+    const i64 tile_step = single ? (i64)gridDim.x : (i64)gridDim.x * GROUPS;
     const bool useC = (p.beta != 0.0);
+    const bool useRed = (p.beta == 1.0) && !(p.flags & 16);  // rank-k update form: C += alpha op(A) op(B)
 
     const int g = lane >> 2, t = lane & 3;
-    const int wm0 = (cw & 1) * 64, wn0 = (cw >> 1) * 32;
+    const int wm0 = (cw % CF::WM) * (8 * FM), wn0 = (cw / CF::WM) * (8 * FN);
 
     // per-lane fragment address pieces (bytes, relative to the operand's stage base)
     //   K-major : row*128 + (((2ks + t/2) ^ (row&7)) << 4) + (t&1)*8,  row = wbase + 8f + PK[g]
@@ -257,7 +286,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_tma_kernel(const __grid_
             ptile = tile; pm0 = tm * TM; pn0 = tn * TN; pkt = 0; pvalid = true;
             break;
         }
-        if (pvalid && useC) {
+        if (pvalid && useC && !useRed) {
             // 64 columns x 128 rows x 8 B: lane handles columns lane and lane + 32
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
@@ -302,11 +331,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_tma_kernel(const __grid_
         if (!tile_active<MODE>(p, tm, tn)) continue;
         const i64 m0 = tm * TM, n0 = tn * TN;
 
-        double acc[8][4][2];
+        double acc[FM][FN][2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < FM; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
         if (stagger && group == 1 && !released) {
             mbar_wait(go_bar, 0);
@@ -325,21 +354,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_tma_kernel(const __grid_
             const unsigned sb = sa + A_BYTES;
 #pragma unroll
             for (int ks = 0; ks < BK / 4; ++ks) {
-                double a[8], b[4];
+                double a[FM], b[FN];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < FM; ++i) {
                     if (A_KMAJOR) a[i] = lds64(sa + aoff[ks] + (unsigned)i * 1024u);
                     else a[i] = lds64(sa + aoff[(i & 1) + 2 * (ks & 1)] + (unsigned)(i >> 1) * 2048u + (unsigned)ks * 512u);
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < FN; ++j) {
                     if (B_KMAJOR) b[j] = lds64(sb + boff[ks] + (unsigned)j * 1024u);
                     else b[j] = lds64(sb + boff[(j & 1) + 2 * (ks & 1)] + (unsigned)(j >> 1) * 2048u + (unsigned)ks * 512u);
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < FM; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + stage * 8);
@@ -354,9 +383,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_tma_kernel(const __grid_
             // fast path (all but the edge / diagonal tiles): no masks, one base pointer per column
             // and compile-time row offsets; two memory round trips per tile
             double* cbase = p.C + (m0 + wm0 + tile_row<A_KMAJOR>(0, g)) + (n0 + wn0) * p.ldc;
+            if (useRed) {
 #pragma unroll
-            for (int jj = 0; jj < 4; jj += 2) {
-                double old[2][2][8];
+                for (int j = 0; j < FN; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        double* cptr = cbase + (i64)tile_row<B_KMAJOR>(j, 2 * t + e) * p.ldc;
+#pragma unroll
+                        for (int i = 0; i < FM; ++i) red_add_f64(cptr + tile_row<A_KMAJOR>(i, 0), __dmul_rn(alpha, acc[i][j][e]));
+                    }
+            } else
+#pragma unroll
+            for (int jj = 0; jj < FN; jj += 2) {
+                double old[2][2][FM];
                 if (useC) {
 #pragma unroll
                     for (int j2 = 0; j2 < 2; ++j2)
@@ -364,7 +403,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_tma_kernel(const __grid_
                         for (int e = 0; e < 2; ++e) {
                             const double* cptr = cbase + (i64)tile_row<B_KMAJOR>(jj + j2, 2 * t + e) * p.ldc;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) old[j2][e][i] = __ldcg(cptr + tile_row<A_KMAJOR>(i, 0));
+                            for (int i = 0; i < FM; ++i) old[j2][e][i] = __ldcg(cptr + tile_row<A_KMAJOR>(i, 0));
                         }
                 }
 #pragma unroll
@@ -373,31 +412,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_tma_kernel(const __grid_
                     for (int e = 0; e < 2; ++e) {
                         double* cptr = cbase + (i64)tile_row<B_KMAJOR>(jj + j2, 2 * t + e) * p.ldc;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            double v = alpha * acc[i][jj + j2][e];
-                            if (useC) v += beta * old[j2][e][i];
+                        for (int i = 0; i < FM; ++i) {
+                            double v = __dmul_rn(alpha, acc[i][jj + j2][e]);
+                            if (useC) v = __fma_rn(beta, old[j2][e][i], v);
                             cptr[tile_row<A_KMAJOR>(i, 0)] = v;
                         }
                     }
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                double old[2][8];
-                bool ok[2][8];
+            for (int j = 0; j < FN; ++j) {
+                double old[2][FM];
+                bool ok[2][FM];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const i64 col = n0 + wn0 + tile_row<B_KMAJOR>(j, 2 * t + e);
                     const i64 gj = p.gj0 + col * p.gjs;
                     const double* cptr = p.C + col * p.ldc;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < FM; ++i) {
                         const i64 row = m0 + wm0 + tile_row<A_KMAJOR>(i, g);
                         bool v = (col < p.n) && (row < p.m);
                         if (MODE == 1) v = v && (p.gi0 + row * p.gis >= gj);
                         if (MODE == 2) v = v && (p.gi0 + row * p.gis <= gj);
                         ok[e][i] = v;
-                        old[e][i] = (v && useC) ? __ldcg(cptr + row) : 0.0;
+                        old[e][i] = (v && useC && !useRed) ? __ldcg(cptr + row) : 0.0;
                     }
                 }
 #pragma unroll
@@ -405,11 +444,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_tma_kernel(const __grid_
                     const i64 col = n0 + wn0 + tile_row<B_KMAJOR>(j, 2 * t + e);
                     double* cptr = p.C + col * p.ldc;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < FM; ++i) {
                         const i64 row = m0 + wm0 + tile_row<A_KMAJOR>(i, g);
                         if (ok[e][i]) {
-                            double v = alpha * acc[i][j][e];
-                            if (useC) v += beta * old[e][i];
+                            double v = __dmul_rn(alpha, acc[i][j][e]);
+                            if (useRed) { red_add_f64(cptr + row, v); continue; }
+                            if (useC) v = __fma_rn(beta, old[e][i], v);
                             cptr[row] = v;
                         }
                     }
@@ -454,10 +494,10 @@ void make_map(CUtensorMap* map, const double* ptr, i64 inner, i64 outer, i64 ld,
     if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
 }
 
-template <bool AK, bool BKM, int MODE>
+template <class CF, bool AK, bool BKM, int MODE>
 void launch(const TmaArgs& a, double flops, cudaStream_t s) {
     static bool configured = false;
-    auto kern = gemm_f64_tma_kernel<AK, BKM, MODE>;
+    auto kern = gemm_f64_tma_kernel<CF, AK, BKM, MODE>;
     if (!configured) {
         ELB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured = true;
@@ -466,20 +506,25 @@ void launch(const TmaArgs& a, double flops, cudaStream_t s) {
     i64 grid = (tiles + GROUPS - 1) / GROUPS;
     if (grid > sm_count()) grid = sm_count();
     gemm_profile_begin(s);
-    kern<<<(unsigned)grid, NTHREADS, SMEM_BYTES, s>>>(a);
+    kern<<<(unsigned)grid, CF::NTHREADS, SMEM_BYTES, s>>>(a);
     ELB_LAUNCH_CHECK();
     gemm_profile_end(s, flops);
 }
 
+template <class CF, int MODE>
+void dispatch_cf(bool ak, bool bk, const TmaArgs& a, double flops, cudaStream_t s) {
+    if (ak) {
+        if (bk) launch<CF, true, true, MODE>(a, flops, s);
+        else launch<CF, true, false, MODE>(a, flops, s);
+    } else {
+        if (bk) launch<CF, false, true, MODE>(a, flops, s);
+        else launch<CF, false, false, MODE>(a, flops, s);
+    }
+}
 template <int MODE>
 void dispatch(bool ak, bool bk, const TmaArgs& a, double flops, cudaStream_t s) {
-    if (ak) {
-        if (bk) launch<true, true, MODE>(a, flops, s);
-        else launch<true, false, MODE>(a, flops, s);
-    } else {
-        if (bk) launch<false, true, MODE>(a, flops, s);
-        else launch<false, false, MODE>(a, flops, s);
-    }
+    if (a.flags & 8) dispatch_cf<Cfg4, MODE>(ak, bk, a, flops, s);
+    else dispatch_cf<Cfg8, MODE>(ak, bk, a, flops, s);
 }
 
 }  // namespace
@@ -492,6 +537,7 @@ bool dgemm_tma_device(int mode, bool ta, bool tb, i64 m, i64 n, i64 k, double al
     if (k <= 0 || m <= 0 || n <= 0) return false;
     if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda & 1) || (ldb & 1)) return false;
     if (m >= (i64(1) << 31) || n >= (i64(1) << 31) || k >= (i64(1) << 31)) return false;
+    if (ceil_div(m, TM) * ceil_div(n, TN) >= (i64(1) << 31) / GROUP_N) return false;
     if (!encode_fn()) return false;
     TmaArgs a;
     // A 'T' is K-major: stored k x m, k contiguous.  A 'N' is MN-major: stored m x k, m contiguous.
