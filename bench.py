@@ -222,6 +222,15 @@ def main():
     L.elb200_gemm_profile(0)
     clocks = sampler.stop() if rank == 0 else None
     stats = El.RedistStats()
+    # DRAM traffic of one rank-nb update launch, from the committed ncu --set full capture of the same
+    # launch shape (profiles/r01_dgemm_update_traffic.json, written by scripts/ncu_traffic.py)
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_dgemm_update_traffic.json")))
+        if prof.get("m") == (n + r - 1) // r and prof.get("n") == (n + c - 1) // c and prof.get("k") == nb:
+            traffic = prof["dram_bytes_per_launch"]
+    except Exception:
+        pass
     flops_step = 2.0 * n ** 3
     value = flops_step * args.steps / (ms * 1e-3) / 1e9
     kernel_tf = kflops.value / (kms.value * 1e-3) / 1e12 if kms.value > 0 else 0.0
@@ -296,8 +305,9 @@ def main():
                        "l2": "operands (8.6 GB each at n=32768) far exceed the 126 MB L2; no flush needed"},
             "frac_of_dmma_peak": value / 1e3 / (dmma_peak_tf * N),
             "roofline": {"bound": "tensor", "achieved": kernel_tf, "peak": dmma_peak_tf, "unit": "TFLOP/s",
-                         "frac": kernel_tf / dmma_peak_tf if dmma_peak_tf else None, "traffic": None,
-                         "kernel": "elb200::gemm_f64_kernel (DMMA.8x8x4)",
+                         "frac": kernel_tf / dmma_peak_tf if dmma_peak_tf else None, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": 8.0 * (lh_ * nb + nb * lw_ + 2.0 * lh_ * lw_),
+                         "kernel": "elb200::gemm_f64_tma_kernel (persistent, TMA-fed DMMA.8x8x4, L2 red epilogue)",
                          "launches": int(kcount.value), "kernel_ms_per_step": kms.value / args.steps,
                          "kernel_share_of_step": kms.value / ms if ms else None,
                          "flops_per_launch": kflops.value / max(kcount.value, 1),
