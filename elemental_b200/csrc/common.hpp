@@ -67,4 +67,14 @@ inline char up(char c) { return (c >= 'a' && c <= 'z') ? char(c - 32) : c; }
 
 int sm_count();
 
+// Concurrency plumbing for the overlapped panel loops (SUMMA-C prefetch, Cholesky look-ahead):
+//   * aux_stream(i): lazily created non-blocking streams of the highest priority; the
+//     redistributions / panel factorisations that run beside a trailing update are enqueued there;
+//   * sm_limit: the persistent GEMM kernels launch at most this many CTAs (0 = one per SM).  A
+//     persistent CTA owns its SM's whole register file, so a concurrent NCCL / pack / potrf kernel
+//     can only run beside it on SMs the GEMM leaves free.
+cudaStream_t aux_stream(int idx);
+int sm_limit();
+void set_sm_limit(int n);
+
 }  // namespace elb200

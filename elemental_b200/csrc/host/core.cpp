@@ -1,6 +1,7 @@
 // Object model of the host layer: runtime state, Grid (NCCL communicators),
 // device-resident Matrix and the runtime-typed element-cyclic DistMatrix.
 // See include/elb200/core.hpp for the reference interfaces each piece mirrors.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -40,6 +41,26 @@ template <> void SetLocalTrrkBlocksize<float>(Int b) { g_localTrrkFloat = b; }
 template <> void SetLocalTrrkBlocksize<double>(Int b) { g_localTrrkDouble = b; }
 template <> void SetLocalTrrkBlocksize<Complex<float>>(Int b) { g_localTrrkCFloat = b; }
 template <> void SetLocalTrrkBlocksize<Complex<double>>(Int b) { g_localTrrkCDouble = b; }
+
+namespace dev {
+int PanelSms(int dflt) {
+    static int v = -2;
+    if (v == -2) {
+        const char* e = std::getenv("ELB200_PANEL_SMS");
+        v = e ? std::atoi(e) : -1;
+    }
+    return v >= 0 ? v : dflt;
+}
+static int g_overlap = -1;
+bool OverlapEnabled() {
+    if (g_overlap < 0) {
+        const char* e = std::getenv("ELB200_OVERLAP");
+        g_overlap = (e && std::atoi(e) == 0) ? 0 : 1;
+    }
+    return g_overlap != 0;
+}
+}  // namespace dev
+void SetOverlap(bool on) { dev::g_overlap = on ? 1 : 0; }
 
 Stream CurrentStream() { return (Stream)elb200::current_stream(); }
 void SetCurrentStream(Stream s) { elb200::set_current_stream((cudaStream_t)s); }
@@ -103,7 +124,14 @@ Grid::Grid(const void* uid, int worldRank, int worldSize, int height, GridOrder 
         if (!uid) LogicError("A multi-process Grid needs the broadcast ncclUniqueId");
         ncclUniqueId id;
         std::memcpy(&id, uid, sizeof(id));
-        ELB_NCCL(ncclCommInitRank(&world_, worldSize, id, worldRank));
+        // The panel gathers run beside a persistent GEMM that leaves only a few SMs free
+        // (dev::PanelSms): keep NCCL's kernels within that budget.  ELB200_NCCL_MAX_CTAS=0 keeps
+        // NCCL's own choice.
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        const char* e = std::getenv("ELB200_NCCL_MAX_CTAS");
+        const int maxCtas = e ? std::atoi(e) : 8;
+        if (maxCtas > 0) { cfg.minCTAs = 1; cfg.maxCTAs = maxCtas; }
+        ELB_NCCL(ncclCommInitRankConfig(&world_, worldSize, id, worldRank, &cfg));
         // column communicator: same grid column, ordered by grid row (Grid.cpp:151-156)
         ELB_NCCL(ncclCommSplit(world_, mrRank_, mcRank_, &mc_.nccl, nullptr));
         // row communicator: same grid row, ordered by grid column

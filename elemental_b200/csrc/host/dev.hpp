@@ -30,6 +30,33 @@ template <typename T> constexpr int Code() { return elb200::dtype_code<D<T>>::va
 
 inline cudaStream_t stream() { return (cudaStream_t)CurrentStream(); }
 
+// ---- helpers of the overlapped panel loops ----
+// RAII: make `s` the layer's current stream (everything the host layer enqueues goes there)
+struct StreamScope {
+    cudaStream_t prev;
+    explicit StreamScope(cudaStream_t s) : prev(stream()) { elb200::set_current_stream(s); }
+    ~StreamScope() { elb200::set_current_stream(prev); }
+};
+// RAII: cap the persistent GEMM kernels at n CTAs (0 = all SMs)
+struct SmLimitScope {
+    int prev;
+    explicit SmLimitScope(int n) : prev(elb200::sm_limit()) { elb200::set_sm_limit(n); }
+    ~SmLimitScope() { elb200::set_sm_limit(prev); }
+};
+struct Event {
+    cudaEvent_t e = nullptr;
+    Event() { ELB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
+    ~Event() { if (e) cudaEventDestroy(e); }
+    Event(const Event&) = delete;
+    Event& operator=(const Event&) = delete;
+    void Record(cudaStream_t s) { ELB_CUDA(cudaEventRecord(e, s)); }
+    void Wait(cudaStream_t s) { ELB_CUDA(cudaStreamWaitEvent(s, e, 0)); }
+};
+// SMs the panel stream gets beside a trailing update; ELB200_PANEL_SMS overrides the default
+int PanelSms(int dflt);
+// 0 disables the overlapped loops (ELB200_OVERLAP=0): everything runs on one stream
+bool OverlapEnabled();
+
 inline void nccl_check(ncclResult_t r, const char* what, const char* file, int line) {
     if (r != ncclSuccess) {
         RuntimeError(std::string("NCCL error in ") + what + " at " + file + ":" + std::to_string(line) + ": " +

@@ -55,64 +55,174 @@ void LocalPotrf(UpperOrLower uplo, Matrix<F>& A, int* info, Int colOffset) {
                                     colOffset, dev::stream());
 }
 
+// SMs handed to the panel stream while the trailing update of the previous step runs.  The panel
+// chain is latency-bound (single-CTA potrf, 32-wide triangular sweeps, small messages) but its
+// solves and copies scale with the local panel height, so the share follows the ratio of the two
+// work estimates (both in SM-seconds): enough SMs that the chain hides under the update, and no
+// more, because every reserved SM is lost to the tensor-pipe update.
 template <typename F>
-void LowerVariant3Blocked(AbstractDistMatrix<F>& A, InfoFlag& info) {
+int LookaheadSms(const Grid& g, Int m2, Int nb, Int m2next) {
+    const int total = elb200::sm_count();
+    const double p = g.Size(), r = g.Height(), c = g.Width();
+    const double cplx = IsComplex<F>::value ? 4.0 : 1.0;
+    // trailing update of this step (lower staircase of m2 x m2, rank nb), per rank, at ~0.2 TF/s per SM
+    const double wUpdate = cplx * double(m2) * double(m2) * double(nb) / p / 0.2e12;
+    // next panel: trsm (m2next x nb x nb per p) at ~0.05 TF/s per SM + 5 panel-sized copies at ~30 GB/s per SM
+    const double wChain = cplx * double(m2next) * double(nb) * double(nb) / p / 0.05e12 +
+                          5.0 * 2.0 * sizeof(F) * double(m2next) * double(nb) * (1.0 / r + 1.0 / c + 1.0 / p) / 3.0 / 30e9;
+    const double tFixed = 0.45e-3 + (p > 1 ? 5 * 40e-6 : 0.0);  // potrf latency + NCCL latencies
+    int best = 4;
+    double bestT = 1e30;
+    for (int R = 4; R <= total / 2; R += 4) {
+        const double t = std::max(wUpdate / (total - R), 2.0 * (tFixed + wChain / R));  // 2x safety on the chain
+        if (t < bestT) { bestT = t; best = R; }
+    }
+    return dev::PanelSms(best);
+}
+
+// One panel step of the lower factorisation on the current stream: factor A11, solve A21 and
+// leave it as A21[MC,*] / A21[MR,*] for the trailing update.
+template <typename F>
+void LowerPanel(AbstractDistMatrix<F>& A, Int k, Int nb, InfoFlag& info, AbstractDistMatrix<F>& A11_STAR_STAR,
+                AbstractDistMatrix<F>& A21_MC_STAR, AbstractDistMatrix<F>& A21_MR_STAR) {
     const Grid& g = A.Grid();
     const Int n = A.Height();
-    const Int bsize = Blocksize();
-    AbstractDistMatrix<F> A11_STAR_STAR(g, STAR, STAR);
-    for (Int k = 0; k < n; k += bsize) {
-        const Int nb = std::min(bsize, n - k);
-        const Int m2 = n - (k + nb);
-        auto A11 = View(A, k, k, nb, nb);
-        Copy(static_cast<const AbstractDistMatrix<F>&>(A11), A11_STAR_STAR);
-        LocalPotrf(LOWER, A11_STAR_STAR.Matrix(), info.dev_, k);
-        Copy(static_cast<const AbstractDistMatrix<F>&>(A11_STAR_STAR), A11);
-        if (m2 <= 0) break;
-        auto A21 = View(A, k + nb, k, m2, nb);
-        auto A22 = View(A, k + nb, k + nb, m2, m2);
-        AbstractDistMatrix<F> A21_VC_STAR(g, VC, STAR), A21_MC_STAR(g, MC, STAR), A21_MR_STAR(g, MR, STAR);
-        A21_VC_STAR.AlignWith(A22);
-        Copy(static_cast<const AbstractDistMatrix<F>&>(A21), A21_VC_STAR);
-        LocalTrsm(RIGHT, LOWER, ADJOINT, NON_UNIT, F(1), A11_STAR_STAR, A21_VC_STAR);
-        A21_MC_STAR.AlignWith(A22);
-        A21_MR_STAR.AlignWith(A22);
-        Copy(static_cast<const AbstractDistMatrix<F>&>(A21_VC_STAR), A21_MC_STAR);
-        Copy(static_cast<const AbstractDistMatrix<F>&>(A21_VC_STAR), A21_MR_STAR);
-        // A22 -= A21 A21^H on the lower staircase
-        LocalTrrk(LOWER, NORMAL, ADJOINT, F(-1), A21_MC_STAR, A21_MR_STAR, F(1), A22);
-        Copy(static_cast<const AbstractDistMatrix<F>&>(A21_MC_STAR), A21);
-    }
+    const Int m2 = n - (k + nb);
+    auto A11 = View(A, k, k, nb, nb);
+    Copy(static_cast<const AbstractDistMatrix<F>&>(A11), A11_STAR_STAR);
+    LocalPotrf(LOWER, A11_STAR_STAR.Matrix(), info.dev_, k);
+    Copy(static_cast<const AbstractDistMatrix<F>&>(A11_STAR_STAR), A11);
+    if (m2 <= 0) return;
+    auto A21 = View(A, k + nb, k, m2, nb);
+    auto A22 = View(A, k + nb, k + nb, m2, m2);
+    AbstractDistMatrix<F> A21_VC_STAR(g, VC, STAR);
+    A21_VC_STAR.AlignWith(A22);
+    Copy(static_cast<const AbstractDistMatrix<F>&>(A21), A21_VC_STAR);
+    LocalTrsm(RIGHT, LOWER, ADJOINT, NON_UNIT, F(1), A11_STAR_STAR, A21_VC_STAR);
+    A21_MC_STAR.AlignWith(A22);
+    A21_MR_STAR.AlignWith(A22);
+    Copy(static_cast<const AbstractDistMatrix<F>&>(A21_VC_STAR), A21_MC_STAR);
+    Copy(static_cast<const AbstractDistMatrix<F>&>(A21_VC_STAR), A21_MR_STAR);
+    Copy(static_cast<const AbstractDistMatrix<F>&>(A21_MC_STAR), A21);
 }
 
 template <typename F>
-void UpperVariant3Blocked(AbstractDistMatrix<F>& A, InfoFlag& info) {
+void UpperPanel(AbstractDistMatrix<F>& A, Int k, Int nb, InfoFlag& info, AbstractDistMatrix<F>& A11_STAR_STAR,
+                AbstractDistMatrix<F>& A12_STAR_MC, AbstractDistMatrix<F>& A12_STAR_MR) {
+    const Grid& g = A.Grid();
+    const Int n = A.Height();
+    const Int m2 = n - (k + nb);
+    auto A11 = View(A, k, k, nb, nb);
+    Copy(static_cast<const AbstractDistMatrix<F>&>(A11), A11_STAR_STAR);
+    LocalPotrf(UPPER, A11_STAR_STAR.Matrix(), info.dev_, k);
+    Copy(static_cast<const AbstractDistMatrix<F>&>(A11_STAR_STAR), A11);
+    if (m2 <= 0) return;
+    auto A12 = View(A, k, k + nb, nb, m2);
+    auto A22 = View(A, k + nb, k + nb, m2, m2);
+    AbstractDistMatrix<F> A12_STAR_VR(g, STAR, VR);
+    A12_STAR_VR.AlignWith(A22);
+    Copy(static_cast<const AbstractDistMatrix<F>&>(A12), A12_STAR_VR);
+    LocalTrsm(LEFT, UPPER, ADJOINT, NON_UNIT, F(1), A11_STAR_STAR, A12_STAR_VR);
+    A12_STAR_MC.AlignWith(A22);
+    A12_STAR_MR.AlignWith(A22);
+    Copy(static_cast<const AbstractDistMatrix<F>&>(A12_STAR_VR), A12_STAR_MC);
+    Copy(static_cast<const AbstractDistMatrix<F>&>(A12_STAR_VR), A12_STAR_MR);
+    Copy(static_cast<const AbstractDistMatrix<F>&>(A12_STAR_MR), A12);
+}
+
+// Right-looking variant 3 with a look-ahead of one panel.  The reference's step
+//   A11 -> potrf;  A21 := A21 A11^-H;  A22 -= A21 A21^H            (LowerVariant3.hpp:70-126)
+// is kept operation for operation; only the trailing update is issued in two pieces -- first the
+// nb columns (rows, for UPPER) that form the next panel, then the rest -- so that the next
+// panel's chain (gather, potrf, trsm, two redistributions: all latency-bound) runs on the panel
+// stream underneath the second, tensor-pipe-bound piece.  Every entry of A22 still receives the
+// same rank-nb products in the same order, so the factor is bit-identical to the unsplit loop.
+template <typename F>
+void Variant3Blocked(UpperOrLower uplo, AbstractDistMatrix<F>& A, InfoFlag& info) {
     const Grid& g = A.Grid();
     const Int n = A.Height();
     const Int bsize = Blocksize();
+    const bool lower = uplo == LOWER;
+    const bool overlap = dev::OverlapEnabled() && n > 2 * bsize;
+    cudaStream_t mainS = dev::stream(), panelS = overlap ? elb200::aux_stream(0) : mainS;
     AbstractDistMatrix<F> A11_STAR_STAR(g, STAR, STAR);
-    for (Int k = 0; k < n; k += bsize) {
+    // lower: P = A21[MC,*], Q = A21[MR,*];  upper: P = A12[*,MC], Q = A12[*,MR]
+    AbstractDistMatrix<F> P[2] = {AbstractDistMatrix<F>(g, lower ? MC : STAR, lower ? STAR : MC),
+                                  AbstractDistMatrix<F>(g, lower ? MC : STAR, lower ? STAR : MC)};
+    AbstractDistMatrix<F> Q[2] = {AbstractDistMatrix<F>(g, lower ? MR : STAR, lower ? STAR : MR),
+                                  AbstractDistMatrix<F>(g, lower ? MR : STAR, lower ? STAR : MR)};
+    dev::Event panelDone[2], nextReady, fork, join;
+    auto panel = [&](Int k, Int nb, int slot) {
+        if (lower) LowerPanel(A, k, nb, info, A11_STAR_STAR, P[slot], Q[slot]);
+        else UpperPanel(A, k, nb, info, A11_STAR_STAR, P[slot], Q[slot]);
+    };
+    // trailing update restricted to the square block of A22 that starts `off` rows/columns in,
+    // or (cols = true) to its first `w` columns (lower) / rows (upper)
+    auto update = [&](Int k, Int nb, int slot, Int off, Int w, bool strip) {
+        const Int m2 = n - (k + nb);
+        const Int base = k + nb;
+        if (lower) {
+            // C = A22(off:, off:off+w or end), A21[MC,*](off:, :), A21[MR,*](off:.., :)
+            const Int rows = m2 - off, cols = strip ? w : m2 - off;
+            if (rows <= 0 || cols <= 0) return;
+            auto C = View(A, base + off, base + off, rows, cols);
+            auto Pv = LockedView(static_cast<const AbstractDistMatrix<F>&>(P[slot]), off, 0, rows, nb);
+            auto Qv = LockedView(static_cast<const AbstractDistMatrix<F>&>(Q[slot]), off, 0, cols, nb);
+            LocalTrrk(LOWER, NORMAL, ADJOINT, F(-1), Pv, Qv, F(1), C);
+        } else {
+            const Int cols = m2 - off, rows = strip ? w : m2 - off;
+            if (rows <= 0 || cols <= 0) return;
+            auto C = View(A, base + off, base + off, rows, cols);
+            auto Pv = LockedView(static_cast<const AbstractDistMatrix<F>&>(P[slot]), 0, off, nb, rows);
+            auto Qv = LockedView(static_cast<const AbstractDistMatrix<F>&>(Q[slot]), 0, off, nb, cols);
+            LocalTrrk(UPPER, ADJOINT, NORMAL, F(-1), Pv, Qv, F(1), C);
+        }
+    };
+
+    if (!overlap) {
+        for (Int k = 0; k < n; k += bsize) {
+            const Int nb = std::min(bsize, n - k);
+            panel(k, nb, 0);
+            update(k, nb, 0, 0, 0, false);
+        }
+        return;
+    }
+
+    fork.Record(mainS);
+    fork.Wait(panelS);
+    {
+        dev::StreamScope onPanel(panelS);
+        panel(0, std::min(bsize, n), 0);
+        panelDone[0].Record(panelS);
+    }
+    Int it = 0;
+    for (Int k = 0; k < n; k += bsize, ++it) {
         const Int nb = std::min(bsize, n - k);
         const Int m2 = n - (k + nb);
-        auto A11 = View(A, k, k, nb, nb);
-        Copy(static_cast<const AbstractDistMatrix<F>&>(A11), A11_STAR_STAR);
-        LocalPotrf(UPPER, A11_STAR_STAR.Matrix(), info.dev_, k);
-        Copy(static_cast<const AbstractDistMatrix<F>&>(A11_STAR_STAR), A11);
+        const int slot = (int)(it & 1);
         if (m2 <= 0) break;
-        auto A12 = View(A, k, k + nb, nb, m2);
-        auto A22 = View(A, k + nb, k + nb, m2, m2);
-        AbstractDistMatrix<F> A12_STAR_VR(g, STAR, VR), A12_STAR_MC(g, STAR, MC), A12_STAR_MR(g, STAR, MR);
-        A12_STAR_VR.AlignWith(A22);
-        Copy(static_cast<const AbstractDistMatrix<F>&>(A12), A12_STAR_VR);
-        LocalTrsm(LEFT, UPPER, ADJOINT, NON_UNIT, F(1), A11_STAR_STAR, A12_STAR_VR);
-        A12_STAR_MC.AlignWith(A22);
-        A12_STAR_MR.AlignWith(A22);
-        Copy(static_cast<const AbstractDistMatrix<F>&>(A12_STAR_VR), A12_STAR_MC);
-        Copy(static_cast<const AbstractDistMatrix<F>&>(A12_STAR_VR), A12_STAR_MR);
-        // A22 -= A12^H A12 on the upper staircase
-        LocalTrrk(UPPER, ADJOINT, NORMAL, F(-1), A12_STAR_MC, A12_STAR_MR, F(1), A22);
-        Copy(static_cast<const AbstractDistMatrix<F>&>(A12_STAR_MR), A12);
+        const Int nbNext = std::min(bsize, m2);
+        panelDone[slot].Wait(mainS);
+        // (a) the strip that becomes the next panel, on all SMs (the panel stream is idle here)
+        update(k, nb, slot, 0, nbNext, true);
+        nextReady.Record(mainS);
+        // (b) next panel chain on the panel stream ...
+        const int reserve = LookaheadSms<F>(g, m2 - nbNext, nb, m2 - nbNext);
+        {
+            dev::StreamScope onPanel(panelS);
+            dev::SmLimitScope lim(reserve);
+            nextReady.Wait(panelS);
+            panel(k + nb, nbNext, slot ^ 1);
+            panelDone[slot ^ 1].Record(panelS);
+        }
+        // (c) ... underneath the rest of this step's trailing update
+        {
+            dev::SmLimitScope lim(std::max(1, elb200::sm_count() - reserve));
+            update(k, nb, slot, nbNext, 0, false);
+        }
     }
+    join.Record(panelS);
+    join.Wait(mainS);
 }
 
 }  // namespace
@@ -133,13 +243,11 @@ void Cholesky(UpperOrLower uplo, AbstractDistMatrix<F>& APre, bool scalapack) {
         // Cholesky(uplo, DistMatrix<F,STAR,STAR>&): redundant local factorisation (Cholesky.cpp:123-126)
         LocalPotrf(uplo, APre.Matrix(), info.dev_, 0);
     } else if (APre.ColDist() == MC && APre.RowDist() == MR) {
-        if (uplo == LOWER) LowerVariant3Blocked(APre, info);
-        else UpperVariant3Blocked(APre, info);
+        Variant3Blocked(uplo, APre, info);
     } else {
         AbstractDistMatrix<F> A(APre.Grid(), MC, MR);
         Copy(static_cast<const AbstractDistMatrix<F>&>(APre), A);
-        if (uplo == LOWER) LowerVariant3Blocked(A, info);
-        else UpperVariant3Blocked(A, info);
+        Variant3Blocked(uplo, A, info);
         Copy(static_cast<const AbstractDistMatrix<F>&>(A), APre);
     }
     if (info.Read() != 0) throw NonHPDMatrixException("A was not numerically HPD");

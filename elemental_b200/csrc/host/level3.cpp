@@ -145,7 +145,10 @@ void FormPanel(Orientation o, const AbstractDistMatrix<T>& X, Int i0, Int j0, In
     }
 }
 
-// Stationary C: rank-nb updates (Gemm/NN.hpp:179-218 and the NT/TN/TT mirrors)
+// Stationary C: rank-nb updates (Gemm/NN.hpp:179-218 and the NT/TN/TT mirrors).
+// On a multi-process grid the panels of step k+1 are gathered on the panel stream (NCCL over
+// NVLink) while the tensor-pipe update of step k runs on the main stream: double-buffered
+// panels, two events per slot.  The persistent GEMM leaves PanelSms() SMs to the gather.
 template <typename T>
 void SummaC(Orientation oA, Orientation oB, T alpha, const AbstractDistMatrix<T>& A, const AbstractDistMatrix<T>& B,
             AbstractDistMatrix<T>& C) {
@@ -153,15 +156,47 @@ void SummaC(Orientation oA, Orientation oB, T alpha, const AbstractDistMatrix<T>
     const Int m = C.Height(), n = C.Width();
     const Int sumDim = (oA == NORMAL) ? A.Width() : A.Height();
     const Int bsize = Blocksize();
-    AbstractDistMatrix<T> A1(g, MC, STAR), B1(g, STAR, MR);
-    A1.AlignWith(C);
-    B1.AlignWith(C);
-    for (Int k = 0; k < sumDim; k += bsize) {
-        const Int nb = std::min(bsize, sumDim - k);
-        FormPanel(oA, A, 0, k, m, nb, A1);  // op(A)(:, k:k+nb) -> [MC,*]
-        FormPanel(oB, B, k, 0, nb, n, B1);  // op(B)(k:k+nb, :) -> [*,MR]
-        LocalGemm(NORMAL, NORMAL, alpha, A1, B1, T(1), C);
+    const Int steps = (sumDim + bsize - 1) / bsize;
+    if (g.Size() == 1 || steps < 2 || !dev::OverlapEnabled()) {
+        AbstractDistMatrix<T> A1(g, MC, STAR), B1(g, STAR, MR);
+        A1.AlignWith(C);
+        B1.AlignWith(C);
+        for (Int k = 0; k < sumDim; k += bsize) {
+            const Int nb = std::min(bsize, sumDim - k);
+            FormPanel(oA, A, 0, k, m, nb, A1);  // op(A)(:, k:k+nb) -> [MC,*]
+            FormPanel(oB, B, k, 0, nb, n, B1);  // op(B)(k:k+nb, :) -> [*,MR]
+            LocalGemm(NORMAL, NORMAL, alpha, A1, B1, T(1), C);
+        }
+        return;
     }
+    cudaStream_t mainS = dev::stream(), panelS = elb200::aux_stream(0);
+    const int reserve = dev::PanelSms(8);
+    const int gemmSms = std::max(1, elb200::sm_count() - reserve);
+    AbstractDistMatrix<T> A1[2] = {AbstractDistMatrix<T>(g, MC, STAR), AbstractDistMatrix<T>(g, MC, STAR)};
+    AbstractDistMatrix<T> B1[2] = {AbstractDistMatrix<T>(g, STAR, MR), AbstractDistMatrix<T>(g, STAR, MR)};
+    dev::Event ready[2], freed[2], fork;
+    for (int s = 0; s < 2; ++s) { A1[s].AlignWith(C); B1[s].AlignWith(C); }
+    fork.Record(mainS);   // A, B (and the scaled C) are final on the main stream from here on
+    fork.Wait(panelS);
+    Int it = 0;
+    for (Int k = 0; k < sumDim; k += bsize, ++it) {
+        const Int nb = std::min(bsize, sumDim - k);
+        const int slot = (int)(it & 1);
+        {
+            dev::StreamScope onPanel(panelS);
+            if (it >= 2) freed[slot].Wait(panelS);
+            FormPanel(oA, A, 0, k, m, nb, A1[slot]);
+            FormPanel(oB, B, k, 0, nb, n, B1[slot]);
+            ready[slot].Record(panelS);
+        }
+        ready[slot].Wait(mainS);
+        {
+            dev::SmLimitScope lim(gemmSms);
+            LocalGemm(NORMAL, NORMAL, alpha, A1[slot], B1[slot], T(1), C);
+        }
+        freed[slot].Record(mainS);
+    }
+    // the panels are released in main-stream order (their last reader)
 }
 
 // Stationary A: panels of op(B), skinny local product, sum-scatter into C

@@ -505,6 +505,7 @@ void launch(const TmaArgs& a, double flops, cudaStream_t s) {
     const i64 tiles = a.tilesM * a.tilesN;
     i64 grid = (tiles + GROUPS - 1) / GROUPS;
     if (grid > sm_count()) grid = sm_count();
+    if (sm_limit() > 0 && grid > sm_limit()) grid = sm_limit();  // leave SMs to a concurrent panel stream
     gemm_profile_begin(s);
     kern<<<(unsigned)grid, CF::NTHREADS, SMEM_BYTES, s>>>(a);
     ELB_LAUNCH_CHECK();

@@ -16,6 +16,21 @@ void set_current_stream(cudaStream_t s) { g_stream = s; }
 
 unsigned long long g_kernel_launches = 0;
 
+static int g_sm_limit = 0;
+int sm_limit() { return g_sm_limit; }
+void set_sm_limit(int n) { g_sm_limit = n < 0 ? 0 : n; }
+
+cudaStream_t aux_stream(int idx) {
+    static cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (idx < 0 || idx >= 4) throw std::logic_error("aux_stream: index out of range");
+    if (!streams[idx]) {
+        int lo = 0, hi = 0;
+        ELB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically smallest = highest priority
+        ELB_CUDA(cudaStreamCreateWithPriority(&streams[idx], cudaStreamNonBlocking, hi));
+    }
+    return streams[idx];
+}
+
 // ---- GEMM launch profiling (off by default) ----
 namespace {
 struct ProfPair { cudaEvent_t a, b; double flops; };
@@ -120,6 +135,8 @@ int elb200_gemm_profile_read(double* total_ms, long long* launches, double* flop
     });
 }
 
+void elb200_set_sm_limit(int n) { elb200::set_sm_limit(n); }
+int elb200_get_sm_limit(void) { return elb200::sm_limit(); }
 void elb200_set_stream(elb200_stream_t s) { elb200::set_current_stream((cudaStream_t)s); }
 elb200_stream_t elb200_get_stream(void) { return (elb200_stream_t)elb200::current_stream(); }
 

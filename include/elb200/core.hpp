@@ -76,6 +76,9 @@ typedef CUstream_st* Stream;
 Stream CurrentStream();
 void SetCurrentStream(Stream s);
 void SynchronizeStream();
+// Overlapped panel loops (SUMMA-C panel prefetch, Cholesky look-ahead) on/off; default on,
+// ELB200_OVERLAP=0 in the environment turns them off.  Results are identical either way.
+void SetOverlap(bool on);
 
 // ---- index math (include/El/core/indexing/impl.hpp) ----
 inline Int Mod(Int a, Int b) { Int r = a % b; return r < 0 ? r + b : r; }

@@ -44,6 +44,11 @@ int elb200_version(void);
 int elb200_device_check(void);
 void elb200_set_stream(elb200_stream_t s);
 elb200_stream_t elb200_get_stream(void);
+/* Cap on the CTAs a persistent GEMM launch may occupy (0 = one per SM).  The overlapped panel
+ * loops of the host layer lower it so that NCCL / pack / potrf kernels of the panel stream find
+ * free SMs beside the trailing update. */
+void elb200_set_sm_limit(int n);
+int elb200_get_sm_limit(void);
 
 /* kernels launched by this library since the last reset (bench.py: "gpu_launches") */
 unsigned long long elb200_launch_count(int reset);
