@@ -1,6 +1,7 @@
 // Object model of the host layer: runtime state, Grid (NCCL communicators),
 // device-resident Matrix and the runtime-typed element-cyclic DistMatrix.
 // See include/elb200/core.hpp for the reference interfaces each piece mirrors.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -50,6 +51,42 @@ int PanelSms(int dflt) {
         v = e ? std::atoi(e) : -1;
     }
     return v >= 0 ? v : dflt;
+}
+bool PhaseTimer::Enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = std::getenv("ELB200_TRACE"); v = (e && std::atoi(e) != 0) ? 1 : 0; }
+    return v != 0;
+}
+PhaseTimer::PhaseTimer() {
+    if (!Enabled()) return;
+    ELB_CUDA(cudaEventCreate(&a));
+    ELB_CUDA(cudaEventCreate(&b));
+}
+PhaseTimer::~PhaseTimer() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+}
+void PhaseTimer::Begin(cudaStream_t s) {
+    if (!a) return;
+    ELB_CUDA(cudaStreamSynchronize(s));
+    ELB_CUDA(cudaEventRecord(a, s));
+}
+void PhaseTimer::End(cudaStream_t s, const char* name) {
+    if (!a) return;
+    ELB_CUDA(cudaEventRecord(b, s));
+    ELB_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    ELB_CUDA(cudaEventElapsedTime(&ms, a, b));
+    for (auto& kv : acc)
+        if (kv.first == name) { kv.second += ms; return; }
+    acc.emplace_back(name, (double)ms);
+}
+void PhaseTimer::Report(const char* title) {
+    if (!a) return;
+    double tot = 0;
+    for (auto& kv : acc) tot += kv.second;
+    std::fprintf(stderr, "[elb200 trace] %s: total %.2f ms\n", title, tot);
+    for (auto& kv : acc) std::fprintf(stderr, "[elb200 trace]   %-28s %10.2f ms  %5.1f%%\n", kv.first.c_str(), kv.second, 100.0 * kv.second / tot);
 }
 static int g_overlap = -1;
 bool OverlapEnabled() {

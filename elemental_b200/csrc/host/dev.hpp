@@ -3,6 +3,10 @@
 #pragma once
 #include <nccl.h>
 
+#include <string>
+#include <utility>
+#include <vector>
+
 #include "../kernels/device_api.hpp"
 #include "elb200/core.hpp"
 #include "elb200_level1.h"
@@ -51,6 +55,18 @@ struct Event {
     Event& operator=(const Event&) = delete;
     void Record(cudaStream_t s) { ELB_CUDA(cudaEventRecord(e, s)); }
     void Wait(cudaStream_t s) { ELB_CUDA(cudaStreamWaitEvent(s, e, 0)); }
+};
+// ELB200_TRACE=1: the factorisation drivers synchronise around each phase and print the summed
+// device time per phase at the end (a diagnostic; it serialises the look-ahead)
+struct PhaseTimer {
+    static bool Enabled();
+    std::vector<std::pair<std::string, double>> acc;
+    cudaEvent_t a = nullptr, b = nullptr;
+    PhaseTimer();
+    ~PhaseTimer();
+    void Begin(cudaStream_t s);
+    void End(cudaStream_t s, const char* name);
+    void Report(const char* title);
 };
 // SMs the panel stream gets beside a trailing update; ELB200_PANEL_SMS overrides the default
 int PanelSms(int dflt);

@@ -84,26 +84,43 @@ int LookaheadSms(const Grid& g, Int m2, Int nb, Int m2next) {
 // leave it as A21[MC,*] / A21[MR,*] for the trailing update.
 template <typename F>
 void LowerPanel(AbstractDistMatrix<F>& A, Int k, Int nb, InfoFlag& info, AbstractDistMatrix<F>& A11_STAR_STAR,
-                AbstractDistMatrix<F>& A21_MC_STAR, AbstractDistMatrix<F>& A21_MR_STAR) {
+                AbstractDistMatrix<F>& A21_MC_STAR, AbstractDistMatrix<F>& A21_MR_STAR, dev::PhaseTimer& tm) {
     const Grid& g = A.Grid();
     const Int n = A.Height();
     const Int m2 = n - (k + nb);
+    cudaStream_t s = dev::stream();
     auto A11 = View(A, k, k, nb, nb);
+    tm.Begin(s);
     Copy(static_cast<const AbstractDistMatrix<F>&>(A11), A11_STAR_STAR);
+    tm.End(s, "A11 -> [*,*]");
+    tm.Begin(s);
     LocalPotrf(LOWER, A11_STAR_STAR.Matrix(), info.dev_, k);
+    tm.End(s, "potrf(A11)");
+    tm.Begin(s);
     Copy(static_cast<const AbstractDistMatrix<F>&>(A11_STAR_STAR), A11);
+    tm.End(s, "A11 <- [*,*]");
     if (m2 <= 0) return;
     auto A21 = View(A, k + nb, k, m2, nb);
     auto A22 = View(A, k + nb, k + nb, m2, m2);
     AbstractDistMatrix<F> A21_VC_STAR(g, VC, STAR);
     A21_VC_STAR.AlignWith(A22);
+    tm.Begin(s);
     Copy(static_cast<const AbstractDistMatrix<F>&>(A21), A21_VC_STAR);
+    tm.End(s, "A21 -> [VC,*]");
+    tm.Begin(s);
     LocalTrsm(RIGHT, LOWER, ADJOINT, NON_UNIT, F(1), A11_STAR_STAR, A21_VC_STAR);
+    tm.End(s, "trsm(A21)");
     A21_MC_STAR.AlignWith(A22);
     A21_MR_STAR.AlignWith(A22);
+    tm.Begin(s);
     Copy(static_cast<const AbstractDistMatrix<F>&>(A21_VC_STAR), A21_MC_STAR);
+    tm.End(s, "A21 [VC,*] -> [MC,*]");
+    tm.Begin(s);
     Copy(static_cast<const AbstractDistMatrix<F>&>(A21_VC_STAR), A21_MR_STAR);
+    tm.End(s, "A21 [VC,*] -> [MR,*]");
+    tm.Begin(s);
     Copy(static_cast<const AbstractDistMatrix<F>&>(A21_MC_STAR), A21);
+    tm.End(s, "A21 <- [MC,*]");
 }
 
 template <typename F>
@@ -143,7 +160,8 @@ void Variant3Blocked(UpperOrLower uplo, AbstractDistMatrix<F>& A, InfoFlag& info
     const Int n = A.Height();
     const Int bsize = Blocksize();
     const bool lower = uplo == LOWER;
-    const bool overlap = dev::OverlapEnabled() && n > 2 * bsize;
+    dev::PhaseTimer tm;
+    const bool overlap = dev::OverlapEnabled() && n > 2 * bsize && !dev::PhaseTimer::Enabled();
     cudaStream_t mainS = dev::stream(), panelS = overlap ? elb200::aux_stream(0) : mainS;
     AbstractDistMatrix<F> A11_STAR_STAR(g, STAR, STAR);
     // lower: P = A21[MC,*], Q = A21[MR,*];  upper: P = A12[*,MC], Q = A12[*,MR]
@@ -153,7 +171,7 @@ void Variant3Blocked(UpperOrLower uplo, AbstractDistMatrix<F>& A, InfoFlag& info
                                   AbstractDistMatrix<F>(g, lower ? MR : STAR, lower ? STAR : MR)};
     dev::Event panelDone[2], nextReady, fork, join;
     auto panel = [&](Int k, Int nb, int slot) {
-        if (lower) LowerPanel(A, k, nb, info, A11_STAR_STAR, P[slot], Q[slot]);
+        if (lower) LowerPanel(A, k, nb, info, A11_STAR_STAR, P[slot], Q[slot], tm);
         else UpperPanel(A, k, nb, info, A11_STAR_STAR, P[slot], Q[slot]);
     };
     // trailing update restricted to the square block of A22 that starts `off` rows/columns in,
@@ -183,8 +201,11 @@ void Variant3Blocked(UpperOrLower uplo, AbstractDistMatrix<F>& A, InfoFlag& info
         for (Int k = 0; k < n; k += bsize) {
             const Int nb = std::min(bsize, n - k);
             panel(k, nb, 0);
+            tm.Begin(mainS);
             update(k, nb, 0, 0, 0, false);
+            tm.End(mainS, "trailing update (trrk)");
         }
+        tm.Report(lower ? "Cholesky LOWER" : "Cholesky UPPER");
         return;
     }
 

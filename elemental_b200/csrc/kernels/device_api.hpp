@@ -32,6 +32,13 @@ void gemm_simt_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, T
                       i64 lda, const T* B, i64 ldb, T beta, T* C, i64 ldc, i64 gi0, i64 gis,
                       i64 gj0, i64 gjs, cudaStream_t s, bool realDiag = false);
 
+// float on the tensor cores: 3xTF32 split, tcgen05.mma kind::tf32, accumulator in TMEM (gemm_tf32.cu).
+// Returns false, launching nothing, when A/B are not 16-byte aligned with ld % 4 == 0.
+bool sgemm_3xtf32_device(char transA, char transB, i64 m, i64 n, i64 k, float alpha, const float* A, i64 lda,
+                         const float* B, i64 ldb, float beta, float* C, i64 ldc, cudaStream_t s);
+int sgemm_mode();        // 0 exact FFMA, 1 3xTF32 (elb200_sgemm_set_mode)
+void sgemm_note_simt();
+
 template <class T>
 void trsm_device(char side, char uplo, char trans, char diag, i64 m, i64 n, T alpha, const T* A,
                  i64 lda, T* B, i64 ldb, cudaStream_t s);

@@ -166,6 +166,12 @@ template <>
 void gemm_device<float>(int mode, char ta, char tb, i64 m, i64 n, i64 k, float alpha, const float* A,
                         i64 lda, const float* B, i64 ldb, float beta, float* C, i64 ldc, i64 gi0,
                         i64 gis, i64 gj0, i64 gjs, cudaStream_t s) {
+    // float: exact FFMA (default) or, when elb200_sgemm_set_mode(1) is in force and the operands meet
+    // TMA's alignment rules, the 3xTF32 tcgen05 kernel (full GEMMs only; the masked TRRK form stays SIMT)
+    if (mode == 0 && sgemm_mode() == 1 && k > 0 &&
+        sgemm_3xtf32_device(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, s))
+        return;
+    sgemm_note_simt();
     gemm_simt_device<float>(mode, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, gi0, gis, gj0, gjs, s);
 }
 template <>
@@ -196,12 +202,6 @@ int elb200_sgemm(char ta, char tb, int64_t m, int64_t n, int64_t k, float alpha,
     return guarded([&] {
         gemm_device<float>(0, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, 1, 0, 1, (cudaStream_t)s);
     });
-}
-// PLACEHOLDER until gemm_tf32.cu (tcgen05 kind::tf32, 3xTF32 split) lands: fails loudly, never
-// silently substitutes another kernel.
-int elb200_sgemm_3xtf32(char, char, int64_t, int64_t, int64_t, float, const float*, int64_t, const float*, int64_t,
-                        float, float*, int64_t, elb200_stream_t) {
-    return guarded([] { throw std::runtime_error("elb200_sgemm_3xtf32: the tcgen05 3xTF32 kernel is not built yet"); });
 }
 int elb200_zgemm(char ta, char tb, int64_t m, int64_t n, int64_t k, elb200_c64 alpha,
                  const elb200_c64* A, int64_t lda, const elb200_c64* B, int64_t ldb, elb200_c64 beta,

@@ -90,6 +90,12 @@ int elb200_sgemm_3xtf32(char transA, char transB, int64_t m, int64_t n, int64_t 
                  float alpha, const float* A, int64_t lda,
                  const float* B, int64_t ldb,
                  float beta, float* C, int64_t ldc, elb200_stream_t s);
+/* Which arithmetic elb200_sgemm / sgemm_ / El::Gemm<float> use for full GEMMs: 0 = exact FFMA
+ * (default), 1 = 3xTF32 on tcgen05 whenever the operands are 16-byte aligned with ld % 4 == 0
+ * (otherwise, and for the masked TRRK form, exact FFMA).  elb200_sgemm_last_kernel: 1 SIMT, 2 tcgen05. */
+void elb200_sgemm_set_mode(int mode);
+int elb200_sgemm_get_mode(void);
+int elb200_sgemm_last_kernel(void);
 
 /* ---- TRRK: triangle-restricted rank-k update --------------------------- */
 /* C_tri := alpha op(A) op(B) + beta C_tri, touching only entries whose GLOBAL
