@@ -7,7 +7,7 @@
 // (elb200_sgemm_set_mode), never a silent substitution.
 //
 // Arithmetic.  Every fp32 operand x is split as x = hi + lo + r with hi = rn_tf32(x),
-// lo = rn_tf32(x - hi) (x - hi is exact in fp32), |r| <= 2^-22 |x|.  The product uses three tensor
+// lo = x - hi (exact in fp32; the tensor core ignores its low 13 bits), |r| <= 2^-22 |x|.  The product uses three tensor
 // passes per k-step, small terms first:
 //     D += A_lo B_hi;   D += A_hi B_lo;   D += A_hi B_hi          (A_lo B_lo ~ 2^-22 is dropped)
 // so each a_ik b_kj carries a relative error of about 3 * 2^-22 before the fp32 accumulation in
@@ -24,8 +24,14 @@
 //               descriptors; tcgen05.commit releases the ring stage and, after the last k-block,
 //               publishes the accumulator; the accumulator is double-buffered in TMEM (2 x 128
 //               columns) so the epilogue of tile i runs under the main loop of tile i+1;
-//   warps 6-9   epilogue: tcgen05.ld 32x32b.x32 (each warp owns its 32-lane TMEM quadrant),
-//               C = alpha * acc + beta * C with rows on lanes (coalesced in column-major C).
+//   warps 6-13  epilogue: tcgen05.ld 32x32b.x16 (a warp owns the 32-lane TMEM quadrant warp % 4 and
+//               one half of the columns), C = alpha * acc + beta * C with rows on lanes (coalesced
+//               in column-major C).
+// The tensor core adds into the fp32 accumulator with truncation (measured: the error of a plain
+// TMEM accumulation grows linearly with k).  The k loop is therefore cut into chunks of 1024: each
+// chunk accumulates in TMEM, the epilogue warps promote it into registers with round-to-nearest
+// adds (the two TMEM accumulators alternate between chunks), so the drift is bounded by the chunk
+// length whatever k is.
 // Operands may be K-major (A 'T', B 'N': k contiguous) or MN-major (A 'N', B 'T'): both are
 // canonical UMMA layouts of the 128-byte swizzle; only the TMA boxes and the descriptor strides
 // differ.  TMA zero-fills ragged m / n / k edges.
@@ -45,7 +51,8 @@ constexpr int BM = 128, BN = 128, BK = 32;   // fp32 elements; BK * 4 B = one 12
 constexpr int STAGES = 3;
 constexpr int OP_BYTES = 128 * BK * 4;       // one 128 x 32 fp32 operand block: 16 KB
 constexpr int STAGE_BYTES = 4 * OP_BYTES;    // A hi | B hi | A lo | B lo
-constexpr int SPLIT_WARPS = 4, EPI_WARPS = 4;
+constexpr int SPLIT_WARPS = 4, EPI_WARPS = 8;
+constexpr int KCHUNK = 32;                   // k-blocks (1024 k) accumulated in TMEM between two promotions
 constexpr int NUM_THREADS = 32 * (2 + SPLIT_WARPS + EPI_WARPS);
 constexpr int TMEM_COLS = 2 * BN;            // two fp32 accumulators of 128 lanes x 128 columns
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
@@ -107,28 +114,30 @@ __device__ __forceinline__ void umma_tf32(unsigned d_tmem, unsigned long long ad
 __device__ __forceinline__ void umma_commit(unsigned bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ unsigned rn_tf32(float x) {
-    unsigned r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// round to nearest (ties away, what cvt.rna.tf32.f32 does) with two full-rate integer operations
+__device__ __forceinline__ unsigned rn_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 
-// Shared-memory matrix descriptor (tcgen05 / "UMMA"), 128-byte swizzle:
+// Shared-memory matrix descriptor (tcgen05 / "UMMA"):
 //   bits [0,14)  start address >> 4        bits [16,30) leading-dimension byte offset >> 4
 //   bits [32,46) stride byte offset >> 4   bits [46,48) descriptor version (1 on sm_100)
-//   bits [61,64) layout type (2 = SWIZZLE_128B)
+//   bits [61,64) layout type (2 = SWIZZLE_128B, 1 = SWIZZLE_128B with 32-byte atoms)
 // K-major block [rows][32 k]: rows are 128 B apart, 8-row swizzle atoms 1024 B apart (stride
 // offset); the leading offset is not used by swizzled K-major layouts (1 by convention).
-// MN-major block: boxes [32 k][32 rows]; k rows 128 B apart, 8-k atoms 1024 B apart (stride
-// offset), 32-row groups one box = 4096 B apart (leading offset).
+// MN-major block: boxes [32 k][32 rows], k rows 128 B apart.  32-bit operands can only be
+// transposed by the tensor core from the 32-byte-atom flavour of the 128-byte swizzle (the
+// plain SWIZZLE_128B MN-major descriptor silently multiplies by zero for kind::tf32 -- measured
+// with scripts/micro/umma_probe.cu): 32-byte chunks XOR (k mod 4), atoms of 4 k = 512 B apart
+// (stride offset), 32-row groups one box = 4096 B apart (leading offset).  TMA writes the same
+// pattern with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
 template <bool KMAJOR>
 __device__ __forceinline__ unsigned long long make_desc(unsigned saddr) {
     const unsigned long long lbo = KMAJOR ? 1ull : (4096ull >> 4);
-    const unsigned long long sbo = 1024ull >> 4;
-    return (unsigned long long)((saddr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+    const unsigned long long sbo = KMAJOR ? (1024ull >> 4) : (512ull >> 4);
+    const unsigned long long layout = KMAJOR ? 2ull : 1ull;
+    return (unsigned long long)((saddr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
-// advance of the start-address field per K=8 step: 32 B inside the swizzle span (K-major) or one
-// 8-row atom = 1024 B (MN-major)
+// advance of the start-address field per K=8 step: 32 B inside the swizzle span (K-major) or two
+// 4-k atoms = 1024 B (MN-major)
 template <bool KMAJOR>
 __device__ __forceinline__ unsigned kstep_units() { return KMAJOR ? 2u : 64u; }
 
@@ -214,31 +223,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sgemm_3xtf32_kernel(const __gr
             const unsigned idesc = make_idesc<A_KMAJOR, B_KMAJOR>();
             int stage = 0;
             unsigned ph = 0;
-            unsigned ti = 0;
-            for (i64 t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
-                const unsigned acc = ti & 1u, aph = (ti >> 1) & 1u;
-                mbar_wait(tempty0 + 8 * acc, aph ^ 1u);  // the epilogue has drained this accumulator
-                tc_fence_after();
-                const unsigned d = tmem_base + acc * BN;
-                for (i64 kb = 0; kb < KB; ++kb) {
-                    mbar_wait(split0 + 8 * stage, ph);
+            unsigned ci = 0;  // chunk counter: accumulator ci & 1
+            for (i64 t = blockIdx.x; t < total; t += gridDim.x) {
+                for (i64 kb0 = 0; kb0 < KB; kb0 += KCHUNK, ++ci) {
+                    const unsigned acc = ci & 1u, aph = (ci >> 1) & 1u;
+                    mbar_wait(tempty0 + 8 * acc, aph ^ 1u);  // the epilogue has drained this accumulator
                     tc_fence_after();
-                    const unsigned sa = base + stage * STAGE_BYTES;
-                    const unsigned long long ahi = make_desc<A_KMAJOR>(sa), bhi = make_desc<B_KMAJOR>(sa + OP_BYTES);
-                    const unsigned long long alo = make_desc<A_KMAJOR>(sa + 2 * OP_BYTES),
-                                             blo = make_desc<B_KMAJOR>(sa + 3 * OP_BYTES);
+                    const unsigned d = tmem_base + acc * BN;
+                    const i64 kb1 = kb0 + KCHUNK < KB ? kb0 + KCHUNK : KB;
+                    for (i64 kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(split0 + 8 * stage, ph);
+                        tc_fence_after();
+                        const unsigned sa = base + stage * STAGE_BYTES;
+                        const unsigned long long ahi = make_desc<A_KMAJOR>(sa), bhi = make_desc<B_KMAJOR>(sa + OP_BYTES);
+                        const unsigned long long alo = make_desc<A_KMAJOR>(sa + 2 * OP_BYTES),
+                                                 blo = make_desc<B_KMAJOR>(sa + 3 * OP_BYTES);
 #pragma unroll
-                    for (int ks = 0; ks < BK / 8; ++ks) {
-                        const unsigned long long ka = (unsigned long long)(ks * kstep_units<A_KMAJOR>());
-                        const unsigned long long kbb = (unsigned long long)(ks * kstep_units<B_KMAJOR>());
-                        umma_tf32(d, alo + ka, bhi + kbb, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-                        umma_tf32(d, ahi + ka, blo + kbb, idesc, 1u);
-                        umma_tf32(d, ahi + ka, bhi + kbb, idesc, 1u);
+                        for (int ks = 0; ks < BK / 8; ++ks) {
+                            const unsigned long long ka = (unsigned long long)(ks * kstep_units<A_KMAJOR>());
+                            const unsigned long long kbb = (unsigned long long)(ks * kstep_units<B_KMAJOR>());
+                            umma_tf32(d, alo + ka, bhi + kbb, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+                            umma_tf32(d, ahi + ka, blo + kbb, idesc, 1u);
+                            umma_tf32(d, ahi + ka, bhi + kbb, idesc, 1u);
+                        }
+                        umma_commit(empty0 + 8 * stage);  // ring stage free once these MMAs have read it
+                        if (++stage == STAGES) { stage = 0; ph ^= 1u; }
                     }
-                    umma_commit(empty0 + 8 * stage);  // ring stage free once these MMAs have read it
-                    if (++stage == STAGES) { stage = 0; ph ^= 1u; }
+                    umma_commit(tfull0 + 8 * acc);  // chunk accumulator complete
                 }
-                umma_commit(tfull0 + 8 * acc);  // accumulator complete
             }
         }
     } else if (warp < 2 + SPLIT_WARPS) {
@@ -259,8 +271,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sgemm_3xtf32_kernel(const __gr
                                  : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3)
                                  : "r"(hi_base + off));
                     const unsigned h0 = rn_tf32(x0), h1 = rn_tf32(x1), h2 = rn_tf32(x2), h3 = rn_tf32(x3);
-                    const unsigned l0 = rn_tf32(x0 - __uint_as_float(h0)), l1 = rn_tf32(x1 - __uint_as_float(h1));
-                    const unsigned l2 = rn_tf32(x2 - __uint_as_float(h2)), l3 = rn_tf32(x3 - __uint_as_float(h3));
+                    const unsigned l0 = __float_as_uint(x0 - __uint_as_float(h0)), l1 = __float_as_uint(x1 - __uint_as_float(h1));
+                    const unsigned l2 = __float_as_uint(x2 - __uint_as_float(h2)), l3 = __float_as_uint(x3 - __uint_as_float(h3));
                     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(hi_base + off), "r"(h0), "r"(h1), "r"(h2),
                                  "r"(h3)
                                  : "memory");
@@ -274,44 +286,60 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sgemm_3xtf32_kernel(const __gr
             }
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> C =====
-        const int q = warp & 3;  // a warp may only touch TMEM lanes [32 (warp % 4), +32)
+        // ===== epilogue: TMEM -> registers (promotion of every k-chunk) -> C =====
+        const int q = warp & 3;                    // a warp may only touch TMEM lanes [32 (warp % 4), +32)
+        const int half = (warp - 2 - SPLIT_WARPS) >> 2;  // columns [64 half, +64) of the tile
         const float alpha = p.alpha, beta = p.beta;
-        unsigned ti = 0;
-        for (i64 t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
-            const i64 m0 = (t % p.tilesM) * BM, n0 = (t / p.tilesM) * BN;
-            const unsigned acc = ti & 1u, aph = (ti >> 1) & 1u;
-            mbar_wait(tfull0 + 8 * acc, aph);
-            tc_fence_after();
-            const i64 row = m0 + q * 32 + lane;
-            const bool rowok = row < p.m;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                unsigned v[32];
-                const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + acc * BN + (unsigned)(c * 32);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c == BN / 32 - 1) {
-                    // the whole accumulator is in registers: hand it back to the MMA warp
-                    tc_fence_before();
-                    mbar_arrive(tempty0 + 8 * acc);
-                }
-                float* cptr = p.C + row + (n0 + c * 32) * p.ldc;
+        unsigned ci = 0;
+        for (i64 t = blockIdx.x; t < total; t += gridDim.x) {
+            const i64 m0 = (t % p.tilesM) * BM, n0 = (t / p.tilesM) * BN + half * 64;
+            float sum[64];
+            for (i64 kb0 = 0; kb0 < KB; kb0 += KCHUNK, ++ci) {
+                const unsigned acc = ci & 1u, aph = (ci >> 1) & 1u;
+                mbar_wait(tfull0 + 8 * acc, aph);
+                tc_fence_after();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (rowok && n0 + c * 32 + j < p.n) {
-                        float r = alpha * __uint_as_float(v[j]);
-                        if (beta != 0.f) r = fmaf(beta, cptr[(i64)j * p.ldc], r);
-                        cptr[(i64)j * p.ldc] = r;
+                for (int c = 0; c < 4; ++c) {
+                    unsigned v[16];
+                    const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + acc * BN + (unsigned)(half * 64 + c * 16);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                          "=r"(v[15])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (kb0 == 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) sum[c * 16 + j] = __uint_as_float(v[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) sum[c * 16 + j] += __uint_as_float(v[j]);
+                    }
+                }
+                // this chunk is in registers: hand the accumulator back to the MMA warp
+                tc_fence_before();
+                mbar_arrive(tempty0 + 8 * acc);
+            }
+            const i64 row = m0 + q * 32 + lane;
+            if (row < p.m) {
+                float* cbase = p.C + row + n0 * p.ldc;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float old[16];
+                    if (beta != 0.f) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            old[j] = (n0 + c * 16 + j < p.n) ? __ldcs(cbase + (i64)(c * 16 + j) * p.ldc) : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (n0 + c * 16 + j < p.n) {
+                            float r = alpha * sum[c * 16 + j];
+                            if (beta != 0.f) r = fmaf(beta, old[j], r);
+                            cbase[(i64)(c * 16 + j) * p.ldc] = r;
+                        }
                     }
                 }
             }
@@ -346,13 +374,14 @@ EncodeTiledFn encode_fn() {
 }
 
 // 2-D f32 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, outer stride ld
-void make_map(CUtensorMap* map, const float* ptr, i64 inner, i64 outer, i64 ld, int boxInner, int boxOuter) {
+void make_map(CUtensorMap* map, const float* ptr, i64 inner, i64 outer, i64 ld, int boxInner, int boxOuter,
+              CUtensorMapSwizzle swizzle) {
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4u};
     cuuint32_t box[2] = {(cuuint32_t)boxInner, (cuuint32_t)boxOuter};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled (f32) failed (code " + std::to_string((int)r) + ")");
 }
@@ -395,10 +424,11 @@ bool sgemm_3xtf32_device(char ta_, char tb_, i64 m, i64 n, i64 k, float alpha, c
     TcArgs a;
     // A 'T'/'C' is stored k x m (k contiguous: K-major); A 'N' is stored m x k (MN-major)
     const bool ak = ta, bk = !tb;
-    if (ak) make_map(&a.mapA, A, k, m, lda, BK, BM);
-    else make_map(&a.mapA, A, m, k, lda, 32, BK);
-    if (bk) make_map(&a.mapB, B, k, n, ldb, BK, BN);
-    else make_map(&a.mapB, B, n, k, ldb, 32, BK);
+    const CUtensorMapSwizzle swK = CU_TENSOR_MAP_SWIZZLE_128B, swMN = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if (ak) make_map(&a.mapA, A, k, m, lda, BK, BM, swK);
+    else make_map(&a.mapA, A, m, k, lda, 32, BK, swMN);
+    if (bk) make_map(&a.mapB, B, k, n, ldb, BK, BN, swK);
+    else make_map(&a.mapB, B, n, k, ldb, 32, BK, swMN);
     a.m = m; a.n = n; a.k = k;
     a.C = C; a.ldc = ldc;
     a.alpha = alpha; a.beta = beta;

@@ -72,8 +72,8 @@ class DevMat:
         return np.array_equal(host[mask], self.host0[mask])
 
 
-def gemm(ta, tb, alpha, A: DevMat, B: DevMat, beta, Cm: DevMat, k):
-    fn = getattr(lib(), f"elb200_{SUF[Cm.dt]}gemm")
+def gemm(ta, tb, alpha, A: DevMat, B: DevMat, beta, Cm: DevMat, k, fn=None):
+    fn = getattr(lib(), fn or f"elb200_{SUF[Cm.dt]}gemm")
     check(fn(ch(ta), ch(tb), i64(Cm.m), i64(Cm.n), i64(k), sc(Cm.dt, alpha), A.ptr, i64(A.ld), B.ptr, i64(B.ld),
              sc(Cm.dt, beta), Cm.ptr, i64(Cm.ld), stream()), "gemm")
 

@@ -58,6 +58,28 @@ def test_gemm_matches_reference_all_variants(El, dt):
                 assert O.gemm_residual(got, ref, k, A, B) <= 1.0, (dt, oa, ob, alg)
 
 
+def test_gemm_float_3xtf32_mode_summa_dot(El):
+    """BASELINE.json configs[4] in miniature: El::Gemm float, tall-skinny k (auto-selects SUMMA_Dot, NN.hpp:305),
+    exact-FFMA mode vs 3xTF32 mode, both against the FP64 product.  Tolerance (north_star):
+    ||C - C_ref||_F / (k eps32 ||A||_F ||B||_F) <= 1, and the mode switch must really change the kernel."""
+    from elemental_b200._lib import lib
+    L = lib()
+    m, n, k = 256, 192, 8192
+    A, B, C0 = O.fill(0, m, k, 1, dtype=np.float32), O.fill(0, k, n, 2, dtype=np.float32), O.fill(0, m, n, 3, dtype=np.float32)
+    ref = 3.0 * (A.astype(np.float64) @ B.astype(np.float64)) + 4.0 * C0
+    errs = {}
+    try:
+        for mode, kern in ((0, 1), (1, 2)):
+            L.elb200_sgemm_set_mode(mode)
+            dA, dB, dC = _dm(El, A), _dm(El, B), _dm(El, C0)
+            El.Gemm(El.NORMAL, El.NORMAL, 3.0, dA, dB, 4.0, dC)
+            assert L.elb200_sgemm_last_kernel() == kern
+            errs[mode] = O.gemm_residual(dC.ToGlobal(), ref, k, A, B)   # eps of float32
+            assert errs[mode] <= 1.0, errs
+    finally:
+        L.elb200_sgemm_set_mode(0)
+
+
 def test_gemm_config1_2048_nb128(El):
     """BASELINE.json configs[0]: Gemm NN double m=n=k=2048 nb=128 on a 1x1 Grid."""
     n = 2048

@@ -265,3 +265,38 @@ def test_dgemm_l2_reduction_epilogue_is_bit_identical():
     L.elb200_dgemm_set_debug_flags(0)
     for a, b in zip(outs[:3], outs[3:]):
         assert np.array_equal(a, b)
+
+
+def test_sgemm_3xtf32_tcgen05_all_orientations():
+    """elb200_sgemm_3xtf32 (tcgen05 kind::tf32, 3-pass operand split, k-chunk promotion) against an FP64
+    product.  Stated tolerance: ||C - C_ref||_F <= 8 * 2^-22 * |alpha| ||A||_F ||B||_F + 2 eps32 |beta| ||C0||_F
+    (every a*b term carries <= 3 * 2^-22 from the dropped lo*lo and the truncated lo; the fp32 accumulation
+    adds the usual random-walk term) -- the same order as the exact-FFMA kernel, checked beside it."""
+    import gpuutil as G
+    rng = np.random.default_rng(7)
+    dt = np.float32
+    for (m, n, k, alpha, beta) in [(128, 128, 32, 1.0, 0.0), (256, 384, 96, 3.0, 4.0), (100, 60, 40, 3.0, 4.0),
+                                   (1000, 900, 1000, 1.0, 1.0), (130, 257, 4100, -1.0, 1.0), (257, 129, 7, 2.0, 0.0)]:
+        for ta in "NT":
+            for tb in "NT":
+                A = G.rand(rng, *((m, k) if ta == "N" else (k, m)), dt)
+                B = G.rand(rng, *((k, n) if tb == "N" else (n, k)), dt)
+                C0 = G.rand(rng, m, n, dt)
+                # TMA needs 16-byte aligned bases and leading dimensions that are multiples of 4
+                lda = (A.shape[0] + 3) // 4 * 4 + 4; ldb = (B.shape[0] + 3) // 4 * 4
+                dA, dB, dC = G.DevMat(A, lda), G.DevMat(B, ldb), G.DevMat(C0, m + 5, offset=1)
+                G.gemm(ta, tb, alpha, dA, dB, beta, dC, k, fn="elb200_sgemm_3xtf32")
+                ref = alpha * (_op(A, ta).astype(np.float64) @ _op(B, tb).astype(np.float64)) + beta * C0.astype(np.float64)
+                got = dC.get().astype(np.float64)
+                tol = 8 * 2.0 ** -22 * abs(alpha) * np.linalg.norm(A) * np.linalg.norm(B) + 2 * G.eps(dt) * abs(beta) * np.linalg.norm(C0)
+                assert np.linalg.norm(got - ref) <= tol, (ta, tb, m, n, k, np.linalg.norm(got - ref) / tol)
+                assert dC.padding_untouched()
+
+
+def test_sgemm_3xtf32_rejects_unaligned_operands_loudly():
+    import gpuutil as G
+    rng = np.random.default_rng(8)
+    A, B, C0 = (G.rand(rng, 64, 64, np.float32) for _ in range(3))
+    dA, dB, dC = G.DevMat(A, 65), G.DevMat(B, 64), G.DevMat(C0, 64)   # lda % 4 != 0
+    with pytest.raises(Exception):
+        G.gemm("N", "N", 1.0, dA, dB, 0.0, dC, 64, fn="elb200_sgemm_3xtf32")
