@@ -46,6 +46,12 @@ def parse():
     ap.add_argument("--potrf-n", type=int, default=65536)
     ap.add_argument("--potrf-nb", type=int, default=256)
     ap.add_argument("--no-potrf", action="store_true")
+    ap.add_argument("--no-hpdsolve", action="store_true", help="skip configs[3] (ZHPDSolve n=32768, 1024 rhs)")
+    ap.add_argument("--no-sgemm", action="store_true", help="skip configs[4] (SGEMM SUMMA_Dot k=262144, FFMA vs 3xTF32)")
+    ap.add_argument("--hpd-n", type=int, default=32768)
+    ap.add_argument("--hpd-rhs", type=int, default=1024)
+    ap.add_argument("--sgemm-mn", type=int, default=8192)
+    ap.add_argument("--sgemm-k", type=int, default=262144)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=12288, help="size of the bounded CPU-baseline sample")
@@ -257,9 +263,101 @@ def main():
         potrf = {"workload": f"El::Cholesky LOWER double HPD n={pn} nb={pnb}", "ms": pms,
                  "value": (pn ** 3 / 3.0) / (pms * 1e-3) / 1e9, "unit": "GFLOP/s",
                  "frac_of_dmma_peak": (pn ** 3 / 3.0) / (pms * 1e-3) / 1e12 / (dmma_peak_tf * N)}
+        # solve check on the factor just computed (the reference's own acceptance test,
+        # tests/lapack_like/Cholesky.cpp:47-82): X = A \ Y, then ||A X - Y||_F / (n eps ||A||_F ||X||_F)
+        try:
+            nrhs = 16
+            Y = El.DistMatrix(np.float64, El.MC, El.MR, grid, pn, nrhs).HashFill(0, 7)
+            X = El.DistMatrix(np.float64, El.MC, El.MR, grid, pn, nrhs).HashFill(0, 7)
+            El.CholeskySolveAfter(El.LOWER, El.NORMAL, H, X)
+            H.HashFill(1, 5, float(pn))          # the original A again
+            El.Gemm(El.NORMAL, El.NORMAL, -1.0, H, X, 1.0, Y)
+            potrf["solve_residual"] = El.FrobeniusNorm(Y) / (pn * 2.0 ** -52 * El.FrobeniusNorm(H) * El.FrobeniusNorm(X))
+            potrf["solve_residual_def"] = "||A X - Y||_F / (n eps ||A||_F ||X||_F), X from cholesky::SolveAfter, 16 rhs"
+            del Y, X
+        except Exception as ex:  # the check must never cost the timing line
+            potrf["solve_residual_error"] = repr(ex)[:200]
         del H
         torch.cuda.empty_cache()
         El.SetBlocksize(nb)
+
+    def _guard(fn, name):
+        try:
+            return fn()
+        except Exception as ex:
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            try:
+                L.elb200_sgemm_set_mode(0)
+            except Exception:
+                pass
+            torch.cuda.empty_cache()
+            return {"workload": name, "error": repr(ex)[:300]}
+
+    # ---- ZHPDSolve (BASELINE.json configs[3]) ----
+    def run_hpd():
+        hpd = None
+        if not args.no_hpdsolve:
+            hn, hr = args.hpd_n, args.hpd_rhs
+            El.SetBlocksize(nb)
+            Az = El.DistMatrix(np.complex128, El.MC, El.MR, grid, hn, hn).HashFill(1, 11, float(hn))
+            Bz = El.DistMatrix(np.complex128, El.MC, El.MR, grid, hn, hr)
+            times = []
+            for it in range(2):
+                Bz.HashFill(0, 13)
+                t = timed(lambda: El.HPDSolve(El.LOWER, El.NORMAL, Az, Bz), 1)
+                if it > 0:
+                    times.append(t)
+            hms = sum(times) / len(times)
+            hflops = 4.0 * (hn ** 3 / 3.0 + 2.0 * hn * hn * hr)
+            hpd = {"workload": f"El::HPDSolve LOWER Complex<double> n={hn} rhs={hr} nb={nb}", "ms": hms,
+                   "value": hflops / (hms * 1e-3) / 1e9, "unit": "GFLOP/s (real flops: 4 (n^3/3 + 2 n^2 rhs))",
+                   "frac_of_dmma_peak": hflops / (hms * 1e-3) / 1e12 / (dmma_peak_tf * N)}
+            Rz = El.DistMatrix(np.complex128, El.MC, El.MR, grid, hn, hr).HashFill(0, 13)
+            El.Gemm(El.NORMAL, El.NORMAL, -1.0, Az, Bz, 1.0, Rz)
+            hpd["residual"] = El.FrobeniusNorm(Rz) / (hn * 2.0 ** -52 * El.FrobeniusNorm(Az) * El.FrobeniusNorm(Bz))
+            hpd["residual_def"] = "||A X - B||_F / (n eps ||A||_F ||X||_F)"
+            del Az, Bz, Rz
+            torch.cuda.empty_cache()
+        return hpd
+
+    # ---- SGEMM SUMMA_Dot (BASELINE.json configs[4]): exact FFMA vs 3xTF32 on tcgen05 ----
+    def run_sg():
+        sg = None
+        if not args.no_sgemm:
+            sm_, sk = args.sgemm_mn, args.sgemm_k
+            El.SetBlocksize(nb)
+            Af = El.DistMatrix(np.float32, El.MC, El.MR, grid, sm_, sk).HashFill(0, 21)
+            Bf = El.DistMatrix(np.float32, El.MC, El.MR, grid, sk, sm_).HashFill(0, 22)
+            Cf = El.DistMatrix(np.float32, El.MC, El.MR, grid, sm_, sm_)
+            # FP64 product of a 64 x 64 corner (host, from gathered views) for the error of each mode
+            bs = min(64, sm_)
+            vA, vB = El.DistMatrix(np.float32, El.MC, El.MR, grid), El.DistMatrix(np.float32, El.MC, El.MR, grid)
+            a_blk = vA.View(Af, 0, 0, bs, sk).ToGlobal().astype(np.float64)
+            b_blk = vB.View(Bf, 0, 0, sk, bs).ToGlobal().astype(np.float64)
+            ref_blk = a_blk @ b_blk
+            den = sk * 2.0 ** -23 * np.linalg.norm(a_blk) * np.linalg.norm(b_blk)
+            sflops = 2.0 * sm_ * sm_ * sk
+            sg = {"workload": f"El::Gemm NN float m=n={sm_} k={sk} GEMM_SUMMA_DOT (auto-selected, NN.hpp:305)",
+                  "unit": "GFLOP/s", "error_def": "||C - C_fp64||_F / (k eps32 ||A||_F ||B||_F) on the leading 64 x 64 block"}
+            try:
+                for mode, name in ((1, "3xtf32_tcgen05"), (0, "exact_ffma")):
+                    L.elb200_sgemm_set_mode(mode)
+                    fn = lambda: El.Gemm(El.NORMAL, El.NORMAL, 1.0, Af, Bf, 0.0, Cf)
+                    timed(fn, 1)
+                    sms = timed(fn, 1 if mode == 0 else 2) / (1 if mode == 0 else 2)
+                    vC = El.DistMatrix(np.float32, El.MC, El.MR, grid)
+                    got = vC.View(Cf, 0, 0, bs, bs).ToGlobal().astype(np.float64)
+                    sg[name] = {"ms": sms, "value": sflops / (sms * 1e-3) / 1e9, "error": float(np.linalg.norm(got - ref_blk) / den),
+                                "kernel": int(L.elb200_sgemm_last_kernel())}
+            finally:
+                L.elb200_sgemm_set_mode(0)
+            del Af, Bf, Cf, vA, vB, vC
+            torch.cuda.empty_cache()
+        return sg
+
+    hpd = _guard(run_hpd, "zhpdsolve") if not args.no_hpdsolve else None
+    sg = _guard(run_sg, "sgemm_dot") if not args.no_sgemm else None
 
     # ---- end-to-end: HOST buffers in, HOST result out, through the public API ----
     e2e = None
@@ -322,6 +420,10 @@ def main():
         }
         if potrf:
             line["dpotrf"] = potrf
+        if hpd:
+            line["zhpdsolve"] = hpd
+        if sg:
+            line["sgemm_dot"] = sg
         if e2e:
             line["e2e"] = e2e
         if cpu:

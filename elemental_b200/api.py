@@ -90,6 +90,11 @@ def PopBlocksizeStack():
     _check(lib().ElPopBlocksizeStack(), "ElPopBlocksizeStack")
 
 
+def SetGemmDotBlocksize(b: int):
+    """Edge of the C blocks of SUMMA_Dot (reference: 2000, Gemm/NN.hpp:233); 0 = sized for HBM."""
+    _check(lib().ElSetGemmDotBlocksize(int(b)), "ElSetGemmDotBlocksize")
+
+
 def Synchronize():
     _check(lib().ElSynchronize(), "ElSynchronize")
 

@@ -92,6 +92,7 @@ ElError ElGridCol(ElConstGrid g, int* v) { return Try([&] { *v = G(g)->Col(); })
 ElError ElGridVCRank(ElConstGrid g, int* v) { return Try([&] { *v = G(g)->VCRank(); }); }
 ElError ElGridVRRank(ElConstGrid g, int* v) { return Try([&] { *v = G(g)->VRRank(); }); }
 
+ElError ElSetGemmDotBlocksize(ElInt b) { return Try([&] { SetGemmDotBlocksize(b); }); }
 ElError ElRedistStats(uint64_t out[7], bool reset) {
     return Try([&] {
         RedistStats& s = GetRedistStats();

@@ -1,6 +1,7 @@
 // Object model of the host layer: runtime state, Grid (NCCL communicators),
 // device-resident Matrix and the runtime-typed element-cyclic DistMatrix.
 // See include/elb200/core.hpp for the reference interfaces each piece mirrors.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,6 +23,16 @@ std::vector<Int>& BlocksizeStack() {
 Int g_localTrrkFloat = 64, g_localTrrkDouble = 64, g_localTrrkCFloat = 64, g_localTrrkCDouble = 64;
 }  // namespace
 Int Blocksize() { return BlocksizeStack().back(); }
+namespace { Int g_dotBlocksize = 0; }
+void SetGemmDotBlocksize(Int bs) {
+    if (bs < 0) LogicError("Dot blocksize must be non-negative");
+    g_dotBlocksize = bs;
+}
+Int GemmDotBlocksize(size_t scalarBytes) {
+    if (g_dotBlocksize > 0) return g_dotBlocksize;
+    const double edge = std::sqrt(double(size_t(1) << 30) / double(scalarBytes));
+    return std::max<Int>(128, Int(edge) / 128 * 128);
+}
 void SetBlocksize(Int b) {
     if (b <= 0) LogicError("Blocksize must be positive");
     BlocksizeStack().back() = b;

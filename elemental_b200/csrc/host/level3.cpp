@@ -249,7 +249,8 @@ void SummaB(Orientation oA, Orientation oB, T alpha, const AbstractDistMatrix<T>
 // and one world reduce-scatter per blockSize x blockSize block of C (Gemm/NN.hpp:226-270)
 template <typename T>
 void SummaDot(Orientation oA, Orientation oB, T alpha, const AbstractDistMatrix<T>& A, const AbstractDistMatrix<T>& B,
-              AbstractDistMatrix<T>& C, Int blockSize = 2000) {
+              AbstractDistMatrix<T>& C) {
+    const Int blockSize = GemmDotBlocksize(sizeof(T));
     const Grid& g = C.Grid();
     const Int m = C.Height(), n = C.Width();
     const Int sumDim = (oA == NORMAL) ? A.Width() : A.Height();

@@ -68,6 +68,12 @@ Int Blocksize();
 void SetBlocksize(Int blocksize);
 void PushBlocksizeStack(Int blocksize);
 void PopBlocksizeStack();
+// Edge of the C blocks SUMMA_Dot forms (the reference hard-codes blockSizeDot = 2000, Gemm/NN.hpp:233, a
+// CPU-cache size).  0 (default) = sized for HBM: the largest multiple of 128 whose replicated block stays
+// within 1 GiB, so an 8192 x 8192 float C is ONE product of 4096 tiles (27.7 waves of 148 SMs) instead of
+// 25 products of 1.7 waves each.  The result does not depend on it (every C entry is a full-k product).
+Int GemmDotBlocksize(size_t scalarBytes);
+void SetGemmDotBlocksize(Int bs);
 template <typename T> Int LocalTrrkBlocksize();            // kept for API parity (default 64);
 template <typename T> void SetLocalTrrkBlocksize(Int bs);  // the masked-GEMM leaf does not need it
 

@@ -58,6 +58,9 @@ ElError ElBlocksize(ElInt* blocksize);
 ElError ElSetBlocksize(ElInt blocksize);
 ElError ElPushBlocksizeStack(ElInt blocksize);
 ElError ElPopBlocksizeStack(void);
+/* edge of the C blocks of SUMMA_Dot (reference: blockSizeDot = 2000 hard-coded, Gemm/NN.hpp:233);
+ * 0 = sized for HBM (default).  Results do not depend on it. */
+ElError ElSetGemmDotBlocksize(ElInt blocksize);
 ElError ElSetStream(elb200_stream_t stream);   /* stream all work is enqueued on */
 ElError ElSynchronize(void);
 

@@ -80,6 +80,23 @@ def test_gemm_float_3xtf32_mode_summa_dot(El):
         L.elb200_sgemm_set_mode(0)
 
 
+def test_gemm_dot_blocksize_does_not_change_the_result(El):
+    """SUMMA_Dot forms C block by block (reference blockSizeDot = 2000, NN.hpp:233); here the block edge is sized
+    for HBM.  Every entry is a full-k product, so small blocks, the reference's 2000 and one block must agree
+    with the reference library and -- up to the tile the entry falls in -- with each other."""
+    m, n, k = 300, 260, 2100
+    A, B, C0 = O.fill(0, m, k, 1), O.fill(0, k, n, 2), O.fill(0, m, n, 3)
+    ref = _ref_gemm("N", "N", 3.0, A, B, 4.0, C0.copy(order="F"), 128, El.GEMM_SUMMA_DOT)
+    try:
+        for bs in (128, 2000, 0):
+            El.SetGemmDotBlocksize(bs)
+            dA, dB, dC = _dm(El, A), _dm(El, B), _dm(El, C0)
+            El.Gemm(El.NORMAL, El.NORMAL, 3.0, dA, dB, 4.0, dC, El.GEMM_SUMMA_DOT)
+            assert O.gemm_residual(dC.ToGlobal(), ref, k, A, B) <= 1.0, bs
+    finally:
+        El.SetGemmDotBlocksize(0)
+
+
 def test_gemm_config1_2048_nb128(El):
     """BASELINE.json configs[0]: Gemm NN double m=n=k=2048 nb=128 on a 1x1 Grid."""
     n = 2048
