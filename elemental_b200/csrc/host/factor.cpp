@@ -70,7 +70,7 @@ int LookaheadSms(const Grid& g, Int m2, Int nb, Int m2next) {
     // next panel: trsm (m2next x nb x nb per p) at ~0.05 TF/s per SM + 5 panel-sized copies at ~30 GB/s per SM
     const double wChain = cplx * double(m2next) * double(nb) * double(nb) / p / 0.05e12 +
                           5.0 * 2.0 * sizeof(F) * double(m2next) * double(nb) * (1.0 / r + 1.0 / c + 1.0 / p) / 3.0 / 30e9;
-    const double tFixed = 0.45e-3 + (p > 1 ? 5 * 40e-6 : 0.0);  // potrf latency + NCCL latencies
+    const double tFixed = 0.25e-3 + (p > 1 ? 5 * 40e-6 : 0.0);  // potrf + fused trsm latency (0.18 + 0.07 ms measured) + NCCL latencies
     int best = 4;
     double bestT = 1e30;
     for (int R = 4; R <= total / 2; R += 4) {

@@ -9,6 +9,8 @@
 // inverted block to its 32 rows (LEFT) or columns (RIGHT) of B and (3) one GEMM
 // on the tensor pipe (gemm_device) updates the rest of B.  All the O(m n^2)
 // flops of the solve are in step (3).
+#include <type_traits>
+
 #include "device_api.hpp"
 #include "elb200_blas.h"
 
@@ -16,6 +18,7 @@ namespace elb200 {
 namespace {
 
 constexpr int TB = 32;
+int g_trsm_flags = 0;  // bit 0: never use the fused slab kernel (debug / A-B timing)
 
 // Inverse of each TB x TB diagonal block of the stored triangle of A (n x n).
 // inv holds nblk dense TB x TB column-major blocks (other triangle zero).
@@ -117,6 +120,117 @@ __global__ void __launch_bounds__(256) apply_inv_kernel(int left, int top, int n
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused right-side solve for the Cholesky panel shape (double): X op(A) = alpha B with op(A) UPPER
+// triangular of order n <= 256 (A lower and transposed: the A21 L11^-T of the right-looking
+// factorisation) and B tall.  The rows of a right-side solve are independent, so ONE launch does the
+// whole block substitution: each CTA keeps a 64-row slab of B in shared memory, and per 32-column
+// block applies the inverted diagonal block and downdates the remaining columns of its slab, both on
+// the FP64 tensor pipe (DMMA.8x8x4 fragments read from shared memory with pitches = 4 mod 16
+// doubles: conflict-free).  The generic path above needs 2 launches per 32-column block; for the
+// 256-wide panel of the hot path that was 17 dependent launches (~165 us whatever the height).
+// ---------------------------------------------------------------------------------------------
+constexpr int SLAB_ROWS = 64, SLAB_MAXN = 256, SLAB_THREADS = 512;
+constexpr int SLAB_PM = TB + 4;  // pitch of the 32-wide operand panels
+
+__device__ __forceinline__ void dmma884_t(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
+// tr: op(A) = A^T (A stored lower) ; else op(A) = A (A stored upper).  inv: TB x TB inverses of the
+// stored diagonal blocks (trtri_diag_kernel).
+__global__ void __launch_bounds__(SLAB_THREADS, 1) trsm_right_slab_kernel(int tr, i64 m, i64 n, double alpha,
+                                                                          const double* __restrict__ A, i64 lda,
+                                                                          const double* __restrict__ inv, double* B,
+                                                                          i64 ldb) {
+    extern __shared__ __align__(16) unsigned char slab_smem[];
+    const int nblk = (int)((n + TB - 1) / TB);
+    const int ncol = nblk * TB;            // padded width
+    const int P = ncol + 4;                // slab pitch (= 4 mod 16 doubles since ncol % 32 == 0)
+    double* S = (double*)slab_smem;        // [SLAB_ROWS][P]
+    double* sI = S + SLAB_ROWS * P;        // [TB][SLAB_PM]      sI[nn][kk] = inv(M_kk)(kk, nn)
+    double* sM = sI + TB * SLAB_PM;        // [ncol - TB][SLAB_PM]  sM[nn][kk] = M(k0 + kk, k0 + TB + nn)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    const i64 i0 = (i64)blockIdx.x * SLAB_ROWS;
+
+    // slab <- alpha * B (zero beyond m and n)
+    for (int e = tid; e < SLAB_ROWS * ncol; e += SLAB_THREADS) {
+        const int r = e % SLAB_ROWS, c = e / SLAB_ROWS;
+        double v = 0.0;
+        if (i0 + r < m && c < n) v = alpha * B[(i0 + r) + (i64)c * ldb];
+        S[r * P + c] = v;
+    }
+    const int rf = warp & 7, hf = warp >> 3;   // row fragment (8 rows) and half (0/1) of this warp
+    const double* Srow = S + (rf * 8 + g) * P;
+    for (int kb = 0; kb < nblk; ++kb) {
+        const int k0 = kb * TB, c0 = k0 + TB, rest = ncol - c0;
+        // operand panels of this block step
+        for (int e = tid; e < TB * TB; e += SLAB_THREADS) {
+            const int nn = e & 31, kk = e >> 5;
+            const double* blk = inv + (i64)kb * TB * TB;
+            sI[nn * SLAB_PM + kk] = tr ? blk[nn + kk * TB] : blk[kk + nn * TB];
+        }
+        for (int e = tid; e < rest * TB; e += SLAB_THREADS) {
+            const int nn = e % rest, kk = e / rest;
+            const i64 row = k0 + kk, col = c0 + nn;   // M(row, col), row < col
+            double v = 0.0;
+            if (row < n && col < n) v = tr ? A[col + row * lda] : A[row + col * lda];
+            sM[nn * SLAB_PM + kk] = v;
+        }
+        __syncthreads();
+        // X_k = S_k inv(M_kk): warp -> 8 rows x 16 columns
+        double x[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int ks = 0; ks < TB / 4; ++ks) {
+            const double a = Srow[k0 + 4 * ks + tq];
+#pragma unroll
+            for (int f = 0; f < 2; ++f) dmma884_t(x[f], a, sI[((hf * 2 + f) * 8 + g) * SLAB_PM + 4 * ks + tq]);
+        }
+        __syncthreads();   // every warp has read S_k
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) S[(rf * 8 + g) * P + k0 + (hf * 2 + f) * 8 + 2 * tq + e] = x[f][e];
+        __syncthreads();
+        // S_rest -= X_k M(k, rest): groups of 4 column fragments per warp
+        const int ngroups = (rest / 8 + 3) / 4;
+        for (int gi = hf; gi < ngroups; gi += 2) {
+            double acc[4][2];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) acc[f][0] = acc[f][1] = 0.0;
+            const int cf0 = gi * 4;
+#pragma unroll
+            for (int ks = 0; ks < TB / 4; ++ks) {
+                const double a = Srow[k0 + 4 * ks + tq];
+#pragma unroll
+                for (int f = 0; f < 4; ++f)
+                    if ((cf0 + f) * 8 < rest) dmma884_t(acc[f], a, sM[((cf0 + f) * 8 + g) * SLAB_PM + 4 * ks + tq]);
+            }
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+                if ((cf0 + f) * 8 < rest) {
+                    double* d = S + (rf * 8 + g) * P + c0 + (cf0 + f) * 8 + 2 * tq;
+                    d[0] -= acc[f][0];
+                    d[1] -= acc[f][1];
+                }
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < SLAB_ROWS * ncol; e += SLAB_THREADS) {
+        const int r = e % SLAB_ROWS, c = e / SLAB_ROWS;
+        if (i0 + r < m && c < n) B[(i0 + r) + (i64)c * ldb] = S[r * P + c];
+    }
+}
+
+size_t slab_smem_bytes(i64 n) {
+    const i64 ncol = ceil_div(n, TB) * TB;
+    return sizeof(double) * (size_t)(SLAB_ROWS * (ncol + 4) + TB * SLAB_PM + (ncol - TB) * SLAB_PM);
+}
+
 }  // namespace
 
 void* scratch_alloc(size_t bytes, cudaStream_t s) {
@@ -153,6 +267,22 @@ static void trsm_core(char side, char uplo, char trans, char diag, i64 m, i64 n,
     const bool tr = trans != 'N';
     const int top = trans == 'N' ? 0 : (trans == 'T' ? 1 : 2);
     const bool eff_lower = (uplo == 'L') != tr;  // op(A) is lower triangular
+    if constexpr (std::is_same<T, double>::value) {
+        // the Cholesky panel shape: one fused launch (see trsm_right_slab_kernel)
+        if (!left && !eff_lower && na <= SLAB_MAXN && !(g_trsm_flags & 1)) {
+            const size_t smem = slab_smem_bytes(na);
+            static size_t configured = 0;
+            if (smem > configured) {
+                ELB_CUDA(cudaFuncSetAttribute(trsm_right_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured = smem;
+            }
+            trsm_right_slab_kernel<<<(unsigned)ceil_div(m, (i64)SLAB_ROWS), SLAB_THREADS, smem, s>>>(
+                tr ? 1 : 0, m, n, 1.0, A, lda, inv, B, ldb);
+            ELB_LAUNCH_CHECK();
+            scratch_free(inv, s);
+            return;
+        }
+    }
     const T one = st::from_real(1), minus_one = st::from_real(-1);
     // forward sweep (block 0 first) when: LEFT & op(A) lower, or RIGHT & op(A) upper
     const bool forward = left ? eff_lower : !eff_lower;
@@ -228,6 +358,7 @@ template void trsm_device<c64_t>(char, char, char, char, i64, i64, c64_t, const 
 
 extern "C" {
 using namespace elb200;
+void elb200_trsm_set_debug_flags(int f) { g_trsm_flags = f; }
 int elb200_dtrsm(char side, char uplo, char trans, char diag, int64_t m, int64_t n, double alpha,
                  const double* A, int64_t lda, double* B, int64_t ldb, elb200_stream_t s) {
     return guarded([&] { trsm_device<double>(side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb, (cudaStream_t)s); });

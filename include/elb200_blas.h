@@ -150,6 +150,8 @@ int elb200_csyrk(char uplo, char trans, int64_t n, int64_t k, elb200_c32 alpha,
                  elb200_stream_t s);
 
 /* ---- TRSM: B := alpha op(A)^-1 B (side 'L') or alpha B op(A)^-1 ('R') --- */
+/* debugging aid: bit 0 = never use the fused single-launch kernel of the right-side panel solve */
+void elb200_trsm_set_debug_flags(int flags);
 int elb200_dtrsm(char side, char uplo, char trans, char diag, int64_t m, int64_t n,
                  double alpha, const double* A, int64_t lda, double* B, int64_t ldb,
                  elb200_stream_t s);
@@ -170,6 +172,9 @@ int elb200_ctrsm(char side, char uplo, char trans, char diag, int64_t m, int64_t
  * still holds 0, so one flag can be shared by a whole factorisation).  The
  * host layer turns a nonzero flag into NonHPDMatrixException
  * (LowerVariant3.hpp:29-30). */
+/* debugging aid: SM clocks spent by thread 0 of the single-CTA potrf kernel in {diagonal block, panel
+ * solve, trailing update} and the number of launches since the last reset */
+int elb200_potrf_phase_clocks(unsigned long long out[4], int reset);
 int elb200_dpotrf(char uplo, int64_t n, double* A, int64_t lda, int* info_dev, elb200_stream_t s);
 int elb200_spotrf(char uplo, int64_t n, float* A, int64_t lda, int* info_dev, elb200_stream_t s);
 int elb200_zpotrf(char uplo, int64_t n, elb200_c64* A, int64_t lda, int* info_dev, elb200_stream_t s);
