@@ -100,9 +100,9 @@ def Synchronize():
 
 
 def RedistStats(reset: bool = False) -> dict:
-    out = (C.c_uint64 * 7)()
+    out = (C.c_uint64 * 8)()
     _check(lib().ElRedistStats(out, C.c_bool(reset)), "ElRedistStats")
-    keys = ("copies", "messages", "bytesSent", "packLaunches", "zeroCopySends", "reduceScatters", "allGathers")
+    keys = ("copies", "messages", "bytesSent", "packLaunches", "zeroCopySends", "reduceScatters", "allGathers", "p2pPushes")
     return dict(zip(keys, [int(x) for x in out]))
 
 

@@ -93,11 +93,11 @@ ElError ElGridVCRank(ElConstGrid g, int* v) { return Try([&] { *v = G(g)->VCRank
 ElError ElGridVRRank(ElConstGrid g, int* v) { return Try([&] { *v = G(g)->VRRank(); }); }
 
 ElError ElSetGemmDotBlocksize(ElInt b) { return Try([&] { SetGemmDotBlocksize(b); }); }
-ElError ElRedistStats(uint64_t out[7], bool reset) {
+ElError ElRedistStats(uint64_t out[8], bool reset) {
     return Try([&] {
         RedistStats& s = GetRedistStats();
         out[0] = s.copies; out[1] = s.messages; out[2] = s.bytesSent; out[3] = s.packLaunches;
-        out[4] = s.zeroCopySends; out[5] = s.reduceScatters; out[6] = s.allGathers;
+        out[4] = s.zeroCopySends; out[5] = s.reduceScatters; out[6] = s.allGathers; out[7] = s.p2pPushes;
         if (reset) s = RedistStats();
     });
 }

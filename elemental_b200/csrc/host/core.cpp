@@ -193,7 +193,65 @@ Grid::Grid(const void* uid, int worldRank, int worldSize, int height, GridOrder 
             ELB_NCCL(ncclCommSplit(world_, 0, vcRank_, &vc_.nccl, nullptr));
         }
         if (height_ == 1) { /* size-1 column comm is valid but never used for collectives */ }
+        SetupP2P(worldSize);
     }
+}
+
+// Allocate this rank's exchange window, publish its IPC handle through one ncclAllGather and map the
+// windows of all peers.  Collective: the path is enabled only if EVERY rank succeeded.
+void Grid::SetupP2P(int worldSize) {
+    const char* e = std::getenv("ELB200_P2P");
+    if (!e || std::atoi(e) == 0 || worldSize > elb200::P2P_MAX_PEERS) return;
+    const char* r = std::getenv("ELB200_P2P_REGION_MB");
+    const size_t regionBytes = (size_t)(r ? std::max(1, std::atoi(r)) : 64) << 20;
+    const size_t bytes = 4096 + (size_t)4 * worldSize * regionBytes;
+    cudaStream_t s = dev::stream();
+    int ok = 1;
+    char* local = nullptr;
+    cudaIpcMemHandle_t mine;
+    if (cudaMalloc((void**)&local, bytes) != cudaSuccess) { ok = 0; local = nullptr; cudaGetLastError(); }
+    if (ok && cudaMemset(local, 0, 4096) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&mine, local) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+    if (!ok) std::memset(&mine, 0, sizeof(mine));
+    ELB_CUDA(cudaDeviceSynchronize());
+    // handles (64 B each) and success flags travel through the world communicator
+    const size_t hs = sizeof(cudaIpcMemHandle_t);
+    char* dbuf = nullptr;
+    ELB_CUDA(cudaMalloc((void**)&dbuf, hs * worldSize + sizeof(int)));
+    ELB_CUDA(cudaMemcpy(dbuf + hs * worldRank_, &mine, hs, cudaMemcpyHostToDevice));
+    ELB_NCCL(ncclAllGather(dbuf + hs * worldRank_, dbuf, hs, ncclInt8, world_, s));
+    std::vector<cudaIpcMemHandle_t> handles(worldSize);
+    ELB_CUDA(cudaStreamSynchronize(s));
+    ELB_CUDA(cudaMemcpy(handles.data(), dbuf, hs * worldSize, cudaMemcpyDeviceToHost));
+    std::vector<char*> peer(worldSize, nullptr);
+    if (ok) {
+        for (int w = 0; w < worldSize && ok; ++w) {
+            if (w == worldRank_) { peer[w] = local; continue; }
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, handles[w], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+            peer[w] = (char*)p;
+        }
+    }
+    int* dflag = (int*)(dbuf + hs * worldSize);
+    ELB_CUDA(cudaMemcpy(dflag, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    ELB_NCCL(ncclAllReduce(dflag, dflag, 1, ncclInt, ncclMin, world_, s));
+    ELB_CUDA(cudaStreamSynchronize(s));
+    int all = 0;
+    ELB_CUDA(cudaMemcpy(&all, dflag, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(dbuf);
+    if (!all) {
+        for (int w = 0; w < worldSize; ++w)
+            if (w != worldRank_ && peer[w]) cudaIpcCloseMemHandle(peer[w]);
+        if (local) cudaFree(local);
+        if (worldRank_ == 0) std::fprintf(stderr, "[elb200] ELB200_P2P=1 but the exchange windows could not be mapped; using NCCL\n");
+        return;
+    }
+    p2p_.regionBytes = regionBytes;
+    p2p_.local = local;
+    p2p_.peer = peer;
+    ELB_CUDA(cudaHostAlloc((void**)&p2p_.error, sizeof(int), cudaHostAllocMapped));
+    *p2p_.error = 0;
+    p2p_.on = true;
 }
 
 Grid::~Grid() {
@@ -205,6 +263,21 @@ Grid::~Grid() {
     destroy(mr_.nccl);
     destroy(vc_.nccl);
     destroy(vr_.nccl);
+    if (p2p_.on) {
+        // nobody may still be writing flags into a window that is about to be unmapped
+        cudaDeviceSynchronize();
+        int* d = nullptr;
+        if (world_ && cudaMalloc((void**)&d, sizeof(int)) == cudaSuccess) {
+            cudaMemset(d, 0, sizeof(int));
+            if (ncclAllReduce(d, d, 1, ncclInt, ncclSum, world_, nullptr) == ncclSuccess) cudaDeviceSynchronize();
+            cudaFree(d);
+        }
+        for (size_t w = 0; w < p2p_.peer.size(); ++w)
+            if ((int)w != worldRank_ && p2p_.peer[w]) cudaIpcCloseMemHandle(p2p_.peer[w]);
+        if (p2p_.local) cudaFree(p2p_.local);
+        if (p2p_.error) cudaFreeHost(p2p_.error);
+        p2p_.on = false;
+    }
     if (world_) ncclCommDestroy(world_);
     world_ = nullptr;
 }

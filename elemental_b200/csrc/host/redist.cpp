@@ -110,6 +110,19 @@ void Redistribute(const AbstractDistMatrix<T>& A, AbstractDistMatrix<T>& B, bool
     struct Wire { int peer; const void* sendPtr; void* recvPtr; size_t sendBytes, recvBytes; };
     std::vector<Wire> wires;
 
+    // ---- peer-memory path (Grid::P2PState): one channel per stream that issues redistributions ----
+    Grid::P2PState& pp = g.P2P();
+    int ch = -1;
+    if (pp.on && p > 1) {
+        if (*pp.error) RuntimeError("peer-memory redistribution: a flag wait timed out (ranks out of step?)");
+        ch = (s == elb200::aux_stream(0)) ? 1 : 0;
+    }
+    const unsigned ep = ch >= 0 ? ++pp.epoch[ch] : 0u;
+    const int meW = g.WorldRank();
+    std::vector<int> p2pDest, p2pSrc;  // world ranks this epoch pushes to / is pushed from
+    struct Push { const void* src; void* dst; size_t bytes; };
+    std::vector<Push> pushes;          // contiguous pieces: copy engine, no SM
+
     // ---- plan ----
     plan::RedistPlan P = plan::BuildRedistPlan(g, h, w, la, ldA, lb, ldB, transpose);
     std::vector<Msg>& sendMsg = P.send;
@@ -121,7 +134,8 @@ void Redistribute(const AbstractDistMatrix<T>& A, AbstractDistMatrix<T>& B, bool
         const int qi = v % r, qj = v / r;
         if (qi == mi && qj == mj) continue;
         const Msg& sm = sendMsg[v];
-        if (!sm.empty && !Contig(sm.s_rs, sm.s_cs, sm.nrows, sm.ncols)) {
+        const bool sendP2P = ch >= 0 && !sm.empty && sizeof(T) * (size_t)sm.count() <= pp.regionBytes;
+        if (!sm.empty && !sendP2P && !Contig(sm.s_rs, sm.s_cs, sm.nrows, sm.ncols)) {
             auto key = std::make_tuple(sm.s_off, sm.s_rs, sm.s_cs, sm.nrows, sm.ncols);
             auto it = packOffset.find(key);
             if (it == packOffset.end()) {
@@ -133,7 +147,8 @@ void Redistribute(const AbstractDistMatrix<T>& A, AbstractDistMatrix<T>& B, bool
             }
         }
         const Msg& rm = recvMsg[v];
-        if (!rm.empty && !(plain && Contig(rm.d_rs, rm.d_cs, rm.nrows, rm.ncols))) {
+        const bool recvP2P = ch >= 0 && !rm.empty && sizeof(T) * (size_t)rm.count() <= pp.regionBytes;
+        if (!rm.empty && !recvP2P && !(plain && Contig(rm.d_rs, rm.d_cs, rm.nrows, rm.ncols))) {
             recvOff[v] = recvElems;
             recvElems += rm.count();
         }
@@ -156,6 +171,7 @@ void Redistribute(const AbstractDistMatrix<T>& A, AbstractDistMatrix<T>& B, bool
             packs.push_back(d);
         }
         LaunchLattices<T>(packs, false, nullptr, false);
+        packs.clear();
     }
     // ---- wire ----
     for (int v = 0; v < p; ++v) {
@@ -166,16 +182,53 @@ void Redistribute(const AbstractDistMatrix<T>& A, AbstractDistMatrix<T>& B, bool
         Wire wv;
         wv.peer = g.WorldRankOf(qi, qj);
         wv.sendPtr = nullptr; wv.recvPtr = nullptr; wv.sendBytes = wv.recvBytes = 0;
-        if (!sm.empty) {
+        const bool sendP2P = ch >= 0 && !sm.empty && sizeof(T) * (size_t)sm.count() <= pp.regionBytes;
+        const bool recvP2P = ch >= 0 && !rm.empty && sizeof(T) * (size_t)rm.count() <= pp.regionBytes;
+        if (sendP2P) {
+            // push this piece into the destination's window: region (channel, epoch parity, my rank)
+            T* dstRemote = (T*)pp.Region(wv.peer, ch, ep, meW);
+            if (Contig(sm.s_rs, sm.s_cs, sm.nrows, sm.ncols)) {
+                pushes.push_back(Push{Abuf + sm.s_off, dstRemote, sizeof(T) * (size_t)sm.count()});
+                st.zeroCopySends++;
+            } else {
+                elb200_lattice d;
+                d.src = Abuf; d.dst = dstRemote;
+                d.nrows = sm.nrows; d.ncols = sm.ncols;
+                d.s_off = sm.s_off; d.s_rs = sm.s_rs; d.s_cs = sm.s_cs;
+                d.d_off = 0; d.d_rs = 1; d.d_cs = sm.nrows;
+                packs.push_back(d);
+            }
+            p2pDest.push_back(wv.peer);
+            st.p2pPushes++;
+            st.messages++;
+            st.bytesSent += sizeof(T) * (size_t)sm.count();
+        }
+        if (recvP2P) {
+            elb200_lattice d;
+            d.src = (const T*)pp.Region(meW, ch, ep, wv.peer); d.dst = Bbuf;
+            d.nrows = rm.nrows; d.ncols = rm.ncols;
+            d.s_off = 0; d.s_rs = 1; d.s_cs = rm.nrows;
+            d.d_off = rm.d_off; d.d_rs = rm.d_rs; d.d_cs = rm.d_cs;
+            unpacks.push_back(d);
+            p2pSrc.push_back(wv.peer);
+        }
+        if ((sm.empty || sendP2P) && (rm.empty || recvP2P)) continue;
+        if (!sm.empty && !sendP2P) {
             wv.sendPtr = sendOff[v] >= 0 ? (const void*)(packBuf + sendOff[v]) : (const void*)(Abuf + sm.s_off);
             wv.sendBytes = sizeof(T) * (size_t)sm.count();
             if (sendOff[v] < 0) st.zeroCopySends++;
         }
-        if (!rm.empty) {
+        if (!rm.empty && !recvP2P) {
             wv.recvPtr = recvOff[v] >= 0 ? (void*)(recvBuf + recvOff[v]) : (void*)(Bbuf + rm.d_off);
             wv.recvBytes = sizeof(T) * (size_t)rm.count();
         }
         wires.push_back(wv);
+    }
+    // remote pack lattices were appended after the local ones were launched: launch them, then the
+    // copy-engine pushes, then the flag exchange ("my pieces have landed" / wait for my sources)
+    if (ch >= 0) {
+        LaunchLattices<T>(packs, false, nullptr, false);
+        for (const Push& pu : pushes) ELB_CUDA(cudaMemcpyAsync(pu.dst, pu.src, pu.bytes, cudaMemcpyDefault, s));
     }
     if (!wires.empty()) {
         if (!g.WorldNccl()) RuntimeError("Multi-rank redistribution without an NCCL communicator");
@@ -189,6 +242,14 @@ void Redistribute(const AbstractDistMatrix<T>& A, AbstractDistMatrix<T>& B, bool
             }
         }
         ELB_NCCL(ncclGroupEnd());
+    }
+    if (ch >= 0) {
+        elb200::P2PFlagOps ops;
+        ops.nsignal = ops.nwait = 0;
+        ops.epoch = ep; ops.wait_value = ep; ops.error = pp.error;
+        for (int w : p2pDest) ops.signal[ops.nsignal++] = pp.Ready(w, ch, meW);
+        for (int w : p2pSrc) ops.wait[ops.nwait++] = pp.Ready(meW, ch, w);
+        elb200::p2p_flags(ops, s);
     }
     // ---- unpack (+ the local part), applying conj / alpha / accumulate ----
     {
@@ -221,6 +282,19 @@ void Redistribute(const AbstractDistMatrix<T>& A, AbstractDistMatrix<T>& B, bool
             unpacks.push_back(d);
         }
         LaunchLattices<T>(unpacks, doConj, alpha == T(1) ? nullptr : &alpha, accumulate);
+    }
+    if (ch >= 0) {
+        // "I have consumed epoch ep" to every peer; the window half of epoch ep + 1 is free once every
+        // peer has consumed epoch ep - 1
+        elb200::P2PFlagOps ops;
+        ops.nsignal = ops.nwait = 0;
+        ops.epoch = ep; ops.wait_value = ep - 1; ops.error = pp.error;
+        for (int w = 0; w < p; ++w) {
+            if (w == meW) continue;
+            ops.signal[ops.nsignal++] = pp.Ack(w, ch, meW);
+            if (ep >= 2) ops.wait[ops.nwait++] = pp.Ack(meW, ch, w);
+        }
+        elb200::p2p_flags(ops, s);
     }
     elb200::scratch_free(packBuf, s);
     elb200::scratch_free(recvBuf, s);

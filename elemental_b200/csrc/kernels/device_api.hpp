@@ -56,6 +56,18 @@ void lattice_copy_device(const T* src, T* dst, i64 nrows, i64 ncols, i64 s_off, 
 // Stream-ordered scratch memory (cudaMallocAsync on the device's default pool,
 // release threshold raised so repeated panel-sized requests are served from cache)
 void* scratch_alloc(size_t bytes, cudaStream_t s);
+
+// flag operations of the peer-memory redistribution path (kernels/p2p.cu): store `epoch` (release, system
+// scope) into every signal[] address, then spin until every wait[] address holds a value >= wait_value
+constexpr int P2P_MAX_PEERS = 64;
+struct P2PFlagOps {
+    unsigned* signal[P2P_MAX_PEERS];
+    const unsigned* wait[P2P_MAX_PEERS];
+    int nsignal, nwait;
+    unsigned epoch, wait_value;
+    int* error;  // pinned host memory: set when a wait times out
+};
+void p2p_flags(const P2PFlagOps& ops, cudaStream_t s);
 void scratch_free(void* p, cudaStream_t s);
 
 template <class T> struct dtype_code;

@@ -86,7 +86,7 @@ struct TmaArgs {
     i64 tilesM, tilesN;
     int flags;  // tuning/debug: bit0 = stagger the two groups, bit1 = always use the masked epilogue,
                 // bit2 = only group 0 works, bit3 = 4 warps per group (warp tile 64 x 32) instead of 8,
-                // bit4 = never use the L2 reduction epilogue
+                // bit4 = never use the L2 reduction epilogue, bit5 / bit6 = one-off start offsets per SM / per group
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -230,6 +230,17 @@ __global__ void __launch_bounds__(CF::NTHREADS, 1) gemm_f64_tma_kernel(const __g
     const i64 total_tiles = p.tilesM * p.tilesN;
     const bool single = (p.flags & 4) != 0;  // experiment: only group 0 works (lone-warp DMMA rate)
     if (single && group == 1) return;
+    // experiment (flags bit 5 / bit 6): every SM runs equally long tiles, so the read-modify-write bursts
+    // of all epilogues coincide; a one-off start offset per SM (bit 5: blockIdx % 4 quarter tiles) and per
+    // group (bit 6: group 1 half a tile later) spreads them for the whole launch.  p.k sets the tile time
+    // (~130 ns of DMMA per k-column of a tile pair).
+    if (p.flags & 96) {
+        unsigned ns = 0;
+        const unsigned tile_ns = (unsigned)(p.k > 2048 ? 2048 : p.k) * 130u;
+        if (p.flags & 32) ns += (blockIdx.x & 3u) * (tile_ns / 4u);
+        if ((p.flags & 64) && group == 1) ns += tile_ns / 2u;
+        for (unsigned waited = 0; waited < ns; waited += 1000u) __nanosleep(1000u);
+    }
     const i64 first_tile = single ? (i64)blockIdx.x : (i64)blockIdx.x * GROUPS + group;
     const i64 tile_step = single ? (i64)gridDim.x : (i64)gridDim.x * GROUPS;
     const bool useC = (p.beta != 0.0);

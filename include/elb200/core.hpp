@@ -151,6 +151,25 @@ public:
     int VCToVR(int vc) const { return (vc / height_) + width_ * (vc % height_); }
     int VRToVC(int vr) const { return (vr / width_) + height_ * (vr % width_); }
 
+    // NVLink peer-memory exchange windows (ELB200_P2P=1): every rank's window is mapped by all its peers
+    // (CUDA IPC); redistributions push their pieces into the destination's window instead of going
+    // through ncclSend/ncclRecv.  Layout of a window: 4 KB of flags, then per channel (stream) two halves
+    // of Size() regions of regionBytes each: half (epoch & 1), region = world rank of the source.
+    struct P2PState {
+        bool on = false;
+        size_t regionBytes = 0;
+        char* local = nullptr;
+        std::vector<char*> peer;   // by world rank; peer[WorldRank()] == local
+        unsigned epoch[2] = {0, 0};
+        int* error = nullptr;      // pinned host flag raised by a timed-out wait
+        unsigned* Ready(int owner, int ch, int src) const { return (unsigned*)(peer[owner] + ch * 256) + src; }
+        unsigned* Ack(int owner, int ch, int src) const { return (unsigned*)(peer[owner] + 1024 + ch * 256) + src; }
+        char* Region(int owner, int ch, unsigned ep, int src) const {
+            return peer[owner] + 4096 + ((size_t)(ch * 2 + (ep & 1u)) * peer.size() + (size_t)src) * regionBytes;
+        }
+    };
+    P2PState& P2P() const { return p2p_; }
+
     static const Grid& Default();  // lazily-built trivial 1x1 grid
     static int DefaultHeight(int gridSize);  // src/core/Grid.cpp:66-72
 
@@ -161,6 +180,8 @@ private:
     GridOrder order_ = COLUMN_MAJOR;
     ncclComm* world_ = nullptr;
     Comm mc_, mr_, vc_, vr_;
+    mutable P2PState p2p_;
+    void SetupP2P(int worldSize);
 };
 
 // stride / rank of a distribution on a grid
@@ -377,7 +398,7 @@ template <typename T> Base<T> MaxNorm(const AbstractDistMatrix<T>& A);
 // Collective statistics of the redistribution engine (for tests and the bench breakdown)
 struct RedistStats {
     uint64_t copies = 0, messages = 0, bytesSent = 0, packLaunches = 0, zeroCopySends = 0,
-             reduceScatters = 0, allGathers = 0;
+             reduceScatters = 0, allGathers = 0, p2pPushes = 0;  // p2pPushes: messages written into a peer's window
 };
 RedistStats& GetRedistStats();
 

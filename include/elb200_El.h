@@ -80,8 +80,8 @@ ElError ElGridVCRank(ElConstGrid grid, int* rank);
 ElError ElGridVRRank(ElConstGrid grid, int* rank);
 
 /* redistribution-engine statistics since the last reset (copies, messages, bytesSent,
- * packLaunches, zeroCopySends, reduceScatters, allGathers) */
-ElError ElRedistStats(uint64_t out[7], bool reset);
+ * packLaunches, zeroCopySends, reduceScatters, allGathers, p2pPushes) */
+ElError ElRedistStats(uint64_t out[8], bool reset);
 
 #define ELB200_DECLARE_TYPE(SUF, SCALAR, REAL)                                                              \
     typedef struct ElDistMatrix_##SUF##Dummy* ElDistMatrix_##SUF;                                           \
