@@ -239,6 +239,16 @@ def main():
         pass
     flops_step = 2.0 * n ** 3
     value = flops_step * args.steps / (ms * 1e-3) / 1e9
+    # configs[1] also names the NT and TN orientations: one timed call each, same operands
+    orient = {}
+    for name, oa, ob in (("NT", El.NORMAL, El.TRANSPOSE), ("TN", El.TRANSPOSE, El.NORMAL)):
+        try:
+            fn = lambda: El.Gemm(oa, ob, 1.0, A, B, 1.0, Cm, El.GEMM_SUMMA_C)
+            timed(fn, 1)
+            oms = timed(fn, 1)
+            orient[name] = {"ms": oms, "value": flops_step / (oms * 1e-3) / 1e9, "unit": "GFLOP/s"}
+        except Exception as ex:
+            orient[name] = {"error": repr(ex)[:200]}
     kernel_tf = kflops.value / (kms.value * 1e-3) / 1e12 if kms.value > 0 else 0.0
 
     # ---- DPOTRF (BASELINE.json configs[2]) ----
@@ -418,6 +428,8 @@ def main():
             "redist": stats,
             "clocks": clocks,
         }
+        if orient:
+            line["dgemm_orientations"] = orient
         if potrf:
             line["dpotrf"] = potrf
         if hpd:

@@ -70,11 +70,13 @@ template <> __device__ __forceinline__ c64_t shfl<c64_t>(c64_t v, int src) {
 }
 
 // per-phase clock counts of the last launches (thread 0; diag, solve, update, launches): a debugging
-// aid read by elb200_potrf_phase_clocks, negligible cost
+// aid read by elb200_potrf_phase_clocks.  Accumulated in registers and written once at the end of the
+// kernel, and only while the profile is switched on (elb200_potrf_phase_clocks(out, reset = 2)).
 __device__ unsigned long long g_potrf_clk[4];
+bool g_potrf_prof = false;
 
 template <class T, bool UPPER>
-__global__ void __launch_bounds__(potrf_threads<T>::value, 1) potrf_kernel(i64 n, T* Aptr, i64 lda, int* info, i64 col_offset) {
+__global__ void __launch_bounds__(potrf_threads<T>::value, 1) potrf_kernel(i64 n, T* Aptr, i64 lda, int* info, i64 col_offset, int prof) {
     constexpr int NT = potrf_threads<T>::value;
     constexpr int LDP = potrf_ldp<T>::value;
     typedef scalar_traits<T> st;
@@ -88,11 +90,16 @@ __global__ void __launch_bounds__(potrf_threads<T>::value, 1) potrf_kernel(i64 n
     const TriView<T, UPPER> V{Aptr, lda};
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    long long tclk = clock64();
+    long long tclk = prof ? clock64() : 0;
+    unsigned long long clk[3] = {0, 0, 0};
     auto lap = [&](int slot) {
-        if (tid == 0) { const long long now = clock64(); g_potrf_clk[slot] += (unsigned long long)(now - tclk); tclk = now; }
+        if (prof && tid == 0) { const long long now = clock64(); clk[slot] += (unsigned long long)(now - tclk); tclk = now; }
     };
-    if (tid == 0) g_potrf_clk[3] += 1;
+    auto flush = [&]() {
+        if (prof && tid == 0) {
+            g_potrf_clk[0] += clk[0]; g_potrf_clk[1] += clk[1]; g_potrf_clk[2] += clk[2]; g_potrf_clk[3] += 1;
+        }
+    };
     for (i64 c0 = 0; c0 < n; c0 += JB) {
         const int w = (int)((n - c0 < JB) ? (n - c0) : JB);
         // ---- (1) diagonal block in shared memory, all threads, ONE barrier per column ----
@@ -257,6 +264,7 @@ __global__ void __launch_bounds__(potrf_threads<T>::value, 1) potrf_kernel(i64 n
         __syncthreads();
         lap(2);
     }
+    flush();
 }
 
 template <class T>
@@ -274,7 +282,7 @@ void launch_potrf(i64 n, T* A, i64 lda, int* info, i64 col_offset, cudaStream_t 
         ELB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    kern<<<1, potrf_threads<T>::value, smem, s>>>(n, A, lda, info, col_offset);
+    kern<<<1, potrf_threads<T>::value, smem, s>>>(n, A, lda, info, col_offset, g_potrf_prof ? 1 : 0);
     ELB_LAUNCH_CHECK();
 }
 
@@ -336,6 +344,7 @@ int elb200_potrf_phase_clocks(unsigned long long out[4], int reset) {
             unsigned long long z[4] = {0, 0, 0, 0};
             ELB_CUDA(cudaMemcpyToSymbol(g_potrf_clk, z, sizeof(z)));
         }
+        g_potrf_prof = reset == 2 ? true : (reset == 3 ? false : g_potrf_prof);
     });
 }
 int elb200_dpotrf(char uplo, int64_t n, double* A, int64_t lda, int* info_dev, elb200_stream_t s) {

@@ -173,7 +173,8 @@ int elb200_ctrsm(char side, char uplo, char trans, char diag, int64_t m, int64_t
  * host layer turns a nonzero flag into NonHPDMatrixException
  * (LowerVariant3.hpp:29-30). */
 /* debugging aid: SM clocks spent by thread 0 of the single-CTA potrf kernel in {diagonal block, panel
- * solve, trailing update} and the number of launches since the last reset */
+ * solve, trailing update} and the number of launches since the last reset.  reset: 0 read only, 1 read and
+ * clear, 2 read, clear and switch the profile ON (off by default), 3 read, clear and switch it off */
 int elb200_potrf_phase_clocks(unsigned long long out[4], int reset);
 int elb200_dpotrf(char uplo, int64_t n, double* A, int64_t lda, int* info_dev, elb200_stream_t s);
 int elb200_spotrf(char uplo, int64_t n, float* A, int64_t lda, int* info_dev, elb200_stream_t s);

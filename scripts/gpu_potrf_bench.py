@@ -20,7 +20,7 @@ for dt, suf in ((torch.float64, "d"), (torch.complex128, "z"), (torch.float32, "
             check(fn(G.ch("L"), G.i64(n), C.c_void_p(w.data_ptr()), G.i64(n), C.c_void_p(info.data_ptr()), G.stream()), "potrf")
         run(work[0]); run(work[1]); torch.cuda.synchronize()
         clk = (C.c_ulonglong * 4)()
-        L.elb200_potrf_phase_clocks(clk, 1)
+        L.elb200_potrf_phase_clocks(clk, 2)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(reps):
@@ -28,7 +28,7 @@ for dt, suf in ((torch.float64, "d"), (torch.complex128, "z"), (torch.float32, "
         e1.record(); torch.cuda.synchronize()
         Lf = torch.tril(work[2].T)           # stored column-major: work is the transpose view
         res = float(torch.linalg.norm(Lf @ Lf.conj().T - H) / torch.linalg.norm(H))
-        L.elb200_potrf_phase_clocks(clk, 1)
+        L.elb200_potrf_phase_clocks(clk, 3)
         print("   clocks per launch: diag %.0f solve %.0f update %.0f (launches %d)" % (clk[0] / max(clk[3], 1), clk[1] / max(clk[3], 1), clk[2] / max(clk[3], 1), clk[3]))
         print(f"potrf {suf} n={n}: {1e3 * e0.elapsed_time(e1) / reps:.1f} us   info={int(info.item())}  ||LL^H-A||/||A||={res:.2e}", flush=True)
 # panel trsm of the Cholesky step: X L^H = A21 with A21 (rows x nb)
