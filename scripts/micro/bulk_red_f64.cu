@@ -55,6 +55,21 @@ int main() {
     cudaMemset(C, 0, sizeof(double) * ld * n);
     cudaFuncSetAttribute(red_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     const long long tilesM = m / 128, tiles = tilesM * (n / 64);
+    // per-SM rates: one CTA (mode 3 uses 4 warps) over 4096 tiles -- is the SM's RED.64 rate near 8 B/clk?
+    for (int mode = 0; mode < 4; ++mode) {
+        const long long t1 = 4096;
+        red_kernel<<<1, 256, 65536>>>(C, ld, tilesM, t1, mode);
+        cudaDeviceSynchronize();
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        red_kernel<<<1, 256, 65536>>>(C, ld, tilesM, t1, mode);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        printf("ONE CTA mode %d: %.3f ms for %lld tiles of 64 KB: %.2f GB/s per SM = %.2f B/clk at 1.965 GHz\n", mode, ms, t1,
+               65536.0 * t1 / ms / 1e6, 65536.0 * t1 / ms / 1e6 / 1.965);
+    }
     for (int mode = 0; mode < 4; ++mode) {
         for (int rep = 0; rep < 3; ++rep) {
             cudaEvent_t e0, e1;
