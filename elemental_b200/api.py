@@ -398,6 +398,44 @@ def Trrk(uplo, orientA, orientB, alpha, A: DistMatrix, B: DistMatrix, beta, Cm: 
            "ElTrrkDist")
 
 
+def Syr2k(uplo, orient, alpha, A: DistMatrix, B: DistMatrix, beta, Cm: DistMatrix):
+    """El::Syr2k (src/blas_like/level3/Syr2k.cpp): C_tri := alpha (op(A) op(B)^T + op(B) op(A)^T) + beta C_tri."""
+    _sync_stream()
+    dt = _same(A, B, Cm).dtype
+    _check(Cm._fn("ElSyr2kDist")(uplo, orient, _scalar(dt, alpha), A._h, B._h, _scalar(dt, beta), Cm._h), "ElSyr2kDist")
+
+
+def Her2k(uplo, orient, alpha, A: DistMatrix, B: DistMatrix, beta, Cm: DistMatrix):
+    """El::Her2k: alpha op(A) op(B)^H + conj(alpha) op(B) op(A)^H + beta C on the triangle (complex types; beta real)."""
+    _sync_stream()
+    dt = _same(A, B, Cm).dtype
+    if dt.kind != "c":
+        return Syr2k(uplo, orient, alpha, A, B, beta, Cm)
+    _check(Cm._fn("ElHer2kDist")(uplo, orient, _scalar(dt, alpha), A._h, B._h, _real(dt, beta), Cm._h), "ElHer2kDist")
+
+
+def Symm(side, uplo, alpha, A: DistMatrix, B: DistMatrix, beta, Cm: DistMatrix):
+    """El::Symm (src/blas_like/level3/Symm.cpp): C := alpha A B + beta C (LEFT) / alpha B A + beta C, A = A^T from `uplo`."""
+    _sync_stream()
+    dt = _same(A, B, Cm).dtype
+    _check(Cm._fn("ElSymmDist")(side, uplo, _scalar(dt, alpha), A._h, B._h, _scalar(dt, beta), Cm._h), "ElSymmDist")
+
+
+def Hemm(side, uplo, alpha, A: DistMatrix, B: DistMatrix, beta, Cm: DistMatrix):
+    _sync_stream()
+    dt = _same(A, B, Cm).dtype
+    if dt.kind != "c":
+        return Symm(side, uplo, alpha, A, B, beta, Cm)
+    _check(Cm._fn("ElHemmDist")(side, uplo, _scalar(dt, alpha), A._h, B._h, _scalar(dt, beta), Cm._h), "ElHemmDist")
+
+
+def Trmm(side, uplo, orient, diag, alpha, A: DistMatrix, B: DistMatrix):
+    """El::Trmm (src/blas_like/level3/Trmm.cpp): B := alpha op(tri(A)) B (LEFT) / alpha B op(tri(A))."""
+    _sync_stream()
+    dt = _same(A, B).dtype
+    _check(B._fn("ElTrmmDist")(side, uplo, orient, diag, _scalar(dt, alpha), A._h, B._h), "ElTrmmDist")
+
+
 def Trsm(side, uplo, orient, diag, alpha, A: DistMatrix, B: DistMatrix):
     _sync_stream()
     dt = _same(A, B).dtype

@@ -207,6 +207,27 @@ ElError ElRedistStats(uint64_t out[8], bool reset) {
                  Sc<T, SCALAR>(alpha), *CM_##SUF(A), *M_##SUF(B));                                                 \
         });                                                                                                        \
     }                                                                                                              \
+    ElError ElSymmDist_##SUF(ElLeftOrRight side, ElUpperOrLower uplo, SCALAR alpha, ElConstDistMatrix_##SUF A,     \
+                             ElConstDistMatrix_##SUF B, SCALAR beta, ElDistMatrix_##SUF C) {                       \
+        return Try([&] {                                                                                           \
+            Symm(static_cast<LeftOrRight>(side), UL(uplo), Sc<T, SCALAR>(alpha), *CM_##SUF(A), *CM_##SUF(B),       \
+                 Sc<T, SCALAR>(beta), *M_##SUF(C), false);                                                         \
+        });                                                                                                        \
+    }                                                                                                              \
+    ElError ElSyr2kDist_##SUF(ElUpperOrLower uplo, ElOrientation o, SCALAR alpha, ElConstDistMatrix_##SUF A,       \
+                              ElConstDistMatrix_##SUF B, SCALAR beta, ElDistMatrix_##SUF C) {                      \
+        return Try([&] {                                                                                           \
+            Syr2k(UL(uplo), O(o), Sc<T, SCALAR>(alpha), *CM_##SUF(A), *CM_##SUF(B), Sc<T, SCALAR>(beta),           \
+                  *M_##SUF(C), false);                                                                             \
+        });                                                                                                        \
+    }                                                                                                              \
+    ElError ElTrmmDist_##SUF(ElLeftOrRight side, ElUpperOrLower uplo, ElOrientation o, ElUnitOrNonUnit diag,       \
+                             SCALAR alpha, ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B) {                      \
+        return Try([&] {                                                                                           \
+            Trmm(static_cast<LeftOrRight>(side), UL(uplo), O(o), static_cast<UnitOrNonUnit>(diag),                 \
+                 Sc<T, SCALAR>(alpha), *CM_##SUF(A), *M_##SUF(B));                                                 \
+        });                                                                                                        \
+    }                                                                                                              \
     ElError ElCholeskyDist_##SUF(ElUpperOrLower uplo, ElDistMatrix_##SUF A) { return Try([&] { Cholesky(UL(uplo), *M_##SUF(A)); }); } \
     ElError ElCholeskySolveAfterDist_##SUF(ElUpperOrLower uplo, ElOrientation o, ElConstDistMatrix_##SUF A,        \
                                            ElDistMatrix_##SUF B) {                                                 \
@@ -221,5 +242,20 @@ ELB200_DEFINE_TYPE(s, float, float, float)
 ELB200_DEFINE_TYPE(d, double, double, double)
 ELB200_DEFINE_TYPE(c, elb200_c32, float, Complex<float>)
 ELB200_DEFINE_TYPE(z, elb200_c64, double, Complex<double>)
+
+#define ELB200_DEFINE_HERMITIAN(SUF, SCALAR, REAL, T)                                                              \
+    ElError ElHemmDist_##SUF(ElLeftOrRight side, ElUpperOrLower uplo, SCALAR alpha, ElConstDistMatrix_##SUF A,     \
+                             ElConstDistMatrix_##SUF B, SCALAR beta, ElDistMatrix_##SUF C) {                       \
+        return Try([&] {                                                                                           \
+            Hemm(static_cast<LeftOrRight>(side), UL(uplo), Sc<T, SCALAR>(alpha), *CM_##SUF(A), *CM_##SUF(B),       \
+                 Sc<T, SCALAR>(beta), *M_##SUF(C));                                                                \
+        });                                                                                                        \
+    }                                                                                                              \
+    ElError ElHer2kDist_##SUF(ElUpperOrLower uplo, ElOrientation o, SCALAR alpha, ElConstDistMatrix_##SUF A,       \
+                              ElConstDistMatrix_##SUF B, REAL beta, ElDistMatrix_##SUF C) {                        \
+        return Try([&] { Her2k(UL(uplo), O(o), Sc<T, SCALAR>(alpha), *CM_##SUF(A), *CM_##SUF(B), beta, *M_##SUF(C)); }); \
+    }
+ELB200_DEFINE_HERMITIAN(c, elb200_c32, float, Complex<float>)
+ELB200_DEFINE_HERMITIAN(z, elb200_c64, double, Complex<double>)
 
 }  // extern "C"

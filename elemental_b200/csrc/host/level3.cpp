@@ -403,6 +403,97 @@ void Herk(UpperOrLower uplo, Orientation o, Base<T> alpha, const AbstractDistMat
     Syrk(uplo, o, T(alpha), A, T(beta), C, true);
 }
 
+
+// ---------------------------------------------------------------------------
+// Syr2k / Her2k, Symm / Hemm, Trmm: compositions over Trrk / Gemm / the redistribution engine
+// ---------------------------------------------------------------------------
+namespace {
+template <typename T> T ConjIf(T a, bool c) { return a; }
+template <> Complex<float> ConjIf(Complex<float> a, bool c) { return c ? std::conj(a) : a; }
+template <> Complex<double> ConjIf(Complex<double> a, bool c) { return c ? std::conj(a) : a; }
+}  // namespace
+
+// C_tri := alpha op(A) op(B)' + alphaSec op(B) op(A)' + beta C_tri, alphaSec = conj(alpha) for Her2k
+// (Syr2k/LN.hpp:25).  The reference fuses both products in LocalTrr2k; two masked rank-k updates do
+// the same arithmetic with one more pass over the triangle of C.
+template <typename T>
+void Syr2k(UpperOrLower uplo, Orientation o, T alpha, const AbstractDistMatrix<T>& A, const AbstractDistMatrix<T>& B,
+           T beta, AbstractDistMatrix<T>& C, bool conjugate) {
+    const Int n = C.Height();
+    const bool normal = (o == NORMAL);
+    if (C.Width() != n || (normal ? A.Height() : A.Width()) != n || (normal ? B.Height() : B.Width()) != n ||
+        (normal ? A.Width() : A.Height()) != (normal ? B.Width() : B.Height()))
+        LogicError("Nonconformal Syr2k");
+    const Orientation other = conjugate ? ADJOINT : TRANSPOSE;
+    const T alphaSec = ConjIf(alpha, conjugate);
+    if (normal) {
+        Trrk(uplo, NORMAL, other, alpha, A, B, beta, C);
+        Trrk(uplo, NORMAL, other, alphaSec, B, A, T(1), C);
+    } else {
+        Trrk(uplo, other, NORMAL, alpha, A, B, beta, C);
+        Trrk(uplo, other, NORMAL, alphaSec, B, A, T(1), C);
+    }
+}
+template <typename T>
+void Her2k(UpperOrLower uplo, Orientation o, T alpha, const AbstractDistMatrix<T>& A, const AbstractDistMatrix<T>& B,
+           Base<T> beta, AbstractDistMatrix<T>& C) {
+    Syr2k(uplo, o, alpha, A, B, T(beta), C, true);
+}
+
+// C := alpha A B + beta C (LEFT) / alpha B A + beta C (RIGHT); only the uplo triangle of A is read.
+// F = tri(A) + strict(tri(A))' is formed once on the device (one transposing redistribution), then
+// the product is an ordinary SUMMA -- all of its flops on the tensor pipe, no triangular special cases.
+template <typename T>
+void Symm(LeftOrRight side, UpperOrLower uplo, T alpha, const AbstractDistMatrix<T>& A, const AbstractDistMatrix<T>& B,
+          T beta, AbstractDistMatrix<T>& C, bool conjugate) {
+    AssertSameGrid(A, C);
+    AssertSameGrid(B, C);
+    const Int m = C.Height(), n = C.Width(), ka = (side == LEFT) ? m : n;
+    if (A.Height() != ka || A.Width() != ka || B.Height() != m || B.Width() != n) LogicError("Nonconformal Symm");
+    const Grid& g = C.Grid();
+    AbstractDistMatrix<T> F(g, MC, MR), Ft(g, MC, MR);
+    Copy(A, F);
+    MakeTrapezoidal(uplo, F, 0);
+    Ft.AlignWith(F);
+    Transpose(static_cast<const AbstractDistMatrix<T>&>(F), Ft, conjugate);
+    // keep only the strict part of the mirrored triangle
+    MakeTrapezoidal(uplo == LOWER ? UPPER : LOWER, Ft, uplo == LOWER ? 1 : -1);
+    Axpy(T(1), static_cast<const AbstractDistMatrix<T>&>(Ft), F);
+    Ft.Empty();
+    if (side == LEFT) Gemm(NORMAL, NORMAL, alpha, static_cast<const AbstractDistMatrix<T>&>(F), B, beta, C, GEMM_DEFAULT);
+    else Gemm(NORMAL, NORMAL, alpha, B, static_cast<const AbstractDistMatrix<T>&>(F), beta, C, GEMM_DEFAULT);
+}
+template <typename T>
+void Hemm(LeftOrRight side, UpperOrLower uplo, T alpha, const AbstractDistMatrix<T>& A, const AbstractDistMatrix<T>& B,
+          T beta, AbstractDistMatrix<T>& C) {
+    Symm(side, uplo, alpha, A, B, beta, C, true);
+}
+
+// B := alpha op(tri(A)) B (LEFT) / alpha B op(tri(A)) (RIGHT).  UNIT: the stored diagonal is never read --
+// the strict triangle multiplies and alpha B is added back.
+template <typename T>
+void Trmm(LeftOrRight side, UpperOrLower uplo, Orientation o, UnitOrNonUnit diag, T alpha,
+          const AbstractDistMatrix<T>& A, AbstractDistMatrix<T>& B) {
+    AssertSameGrid(A, B);
+    const Int m = B.Height(), n = B.Width(), ka = (side == LEFT) ? m : n;
+    if (A.Height() != ka || A.Width() != ka) LogicError("Nonconformal Trmm");
+    const Grid& g = B.Grid();
+    AbstractDistMatrix<T> Tm(g, MC, MR), B0(g, MC, MR);
+    Copy(A, Tm);
+    const bool unit = (diag == UNIT);
+    MakeTrapezoidal(uplo, Tm, unit ? (uplo == LOWER ? -1 : 1) : 0);
+    B0.AlignWith(B);
+    Copy(static_cast<const AbstractDistMatrix<T>&>(B), B0);
+    const T beta = unit ? alpha : T(0);   // unit diagonal: B := alpha (strict B0 + B0)
+    if (unit) { /* B already holds B0; it is scaled by beta = alpha inside Gemm */ }
+    if (side == LEFT)
+        Gemm(o, NORMAL, alpha, static_cast<const AbstractDistMatrix<T>&>(Tm), static_cast<const AbstractDistMatrix<T>&>(B0),
+             beta, B, GEMM_DEFAULT);
+    else
+        Gemm(NORMAL, o, alpha, static_cast<const AbstractDistMatrix<T>&>(B0), static_cast<const AbstractDistMatrix<T>&>(Tm),
+             beta, B, GEMM_DEFAULT);
+}
+
 // ---------------------------------------------------------------------------
 // Trsm
 // ---------------------------------------------------------------------------
@@ -533,6 +624,16 @@ void Trsm(LeftOrRight side, UpperOrLower uplo, Orientation o, UnitOrNonUnit diag
     template void Syrk(UpperOrLower, Orientation, T, const AbstractDistMatrix<T>&, T, AbstractDistMatrix<T>&, bool); \
     template void Herk(UpperOrLower, Orientation, Base<T>, const Matrix<T>&, Base<T>, Matrix<T>&);                   \
     template void Herk(UpperOrLower, Orientation, Base<T>, const AbstractDistMatrix<T>&, Base<T>,                    \
+                       AbstractDistMatrix<T>&);                                                                      \
+    template void Syr2k(UpperOrLower, Orientation, T, const AbstractDistMatrix<T>&, const AbstractDistMatrix<T>&, T, \
+                        AbstractDistMatrix<T>&, bool);                                                               \
+    template void Her2k(UpperOrLower, Orientation, T, const AbstractDistMatrix<T>&, const AbstractDistMatrix<T>&,    \
+                        Base<T>, AbstractDistMatrix<T>&);                                                            \
+    template void Symm(LeftOrRight, UpperOrLower, T, const AbstractDistMatrix<T>&, const AbstractDistMatrix<T>&, T,  \
+                       AbstractDistMatrix<T>&, bool);                                                                \
+    template void Hemm(LeftOrRight, UpperOrLower, T, const AbstractDistMatrix<T>&, const AbstractDistMatrix<T>&, T,  \
+                       AbstractDistMatrix<T>&);                                                                      \
+    template void Trmm(LeftOrRight, UpperOrLower, Orientation, UnitOrNonUnit, T, const AbstractDistMatrix<T>&,       \
                        AbstractDistMatrix<T>&);                                                                      \
     template void Trsm(LeftOrRight, UpperOrLower, Orientation, UnitOrNonUnit, T, const Matrix<T>&, Matrix<T>&, bool); \
     template void Trsm(LeftOrRight, UpperOrLower, Orientation, UnitOrNonUnit, T, const AbstractDistMatrix<T>&,       \

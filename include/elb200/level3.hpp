@@ -53,6 +53,26 @@ template <typename T>
 void Herk(UpperOrLower uplo, Orientation orientation, Base<T> alpha, const AbstractDistMatrix<T>& A, Base<T> beta,
           AbstractDistMatrix<T>& C);
 
+// ---- Syr2k / Her2k, Symm / Hemm, Trmm (siblings over the same leaves) ----
+// Reference: src/blas_like/level3/Syr2k.cpp + Syr2k/{LN,LT,UN,UT}.hpp (LocalTrr2k), Symm.cpp + Symm/*.hpp,
+// Trmm.cpp + Trmm/*.hpp.  Here: Syr2k = two masked rank-k updates (Trrk); Symm = Gemm on the mirrored
+// triangle (an n x n temporary: sized for HBM, not for a CPU cache); Trmm = Gemm on the trapezoid copy.
+template <typename T>
+void Syr2k(UpperOrLower uplo, Orientation orientation, T alpha, const AbstractDistMatrix<T>& A,
+           const AbstractDistMatrix<T>& B, T beta, AbstractDistMatrix<T>& C, bool conjugate = false);
+template <typename T>
+void Her2k(UpperOrLower uplo, Orientation orientation, T alpha, const AbstractDistMatrix<T>& A,
+           const AbstractDistMatrix<T>& B, Base<T> beta, AbstractDistMatrix<T>& C);
+template <typename T>
+void Symm(LeftOrRight side, UpperOrLower uplo, T alpha, const AbstractDistMatrix<T>& A, const AbstractDistMatrix<T>& B,
+          T beta, AbstractDistMatrix<T>& C, bool conjugate = false);
+template <typename T>
+void Hemm(LeftOrRight side, UpperOrLower uplo, T alpha, const AbstractDistMatrix<T>& A, const AbstractDistMatrix<T>& B,
+          T beta, AbstractDistMatrix<T>& C);
+template <typename T>
+void Trmm(LeftOrRight side, UpperOrLower uplo, Orientation orientation, UnitOrNonUnit diag, T alpha,
+          const AbstractDistMatrix<T>& A, AbstractDistMatrix<T>& B);
+
 // ---- Trsm (src/blas_like/level3/Trsm.cpp:24-398, Trsm/{LLN,LLT,LUN,LUT,RLN,RLT,RUN,RUT}.hpp) ----
 template <typename F>
 void Trsm(LeftOrRight side, UpperOrLower uplo, Orientation orientation, UnitOrNonUnit diag, F alpha,

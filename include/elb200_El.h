@@ -146,6 +146,16 @@ ElError ElRedistStats(uint64_t out[8], bool reset);
     ElError ElTrsmDist_##SUF(ElLeftOrRight side, ElUpperOrLower uplo, ElOrientation orientation,            \
                              ElUnitOrNonUnit diag, SCALAR alpha, ElConstDistMatrix_##SUF A,                 \
                              ElDistMatrix_##SUF B);                                                         \
+    /* siblings over the same leaves (include/El/blas_like/level3.h:371-374 Symm, :477-480 Syr2k,           \
+       :559-562 Trmm) */                                                                                    \
+    ElError ElSymmDist_##SUF(ElLeftOrRight side, ElUpperOrLower uplo, SCALAR alpha, ElConstDistMatrix_##SUF A, \
+                             ElConstDistMatrix_##SUF B, SCALAR beta, ElDistMatrix_##SUF C);                 \
+    ElError ElSyr2kDist_##SUF(ElUpperOrLower uplo, ElOrientation orientation, SCALAR alpha,                 \
+                              ElConstDistMatrix_##SUF A, ElConstDistMatrix_##SUF B, SCALAR beta,            \
+                              ElDistMatrix_##SUF C);                                                        \
+    ElError ElTrmmDist_##SUF(ElLeftOrRight side, ElUpperOrLower uplo, ElOrientation orientation,            \
+                             ElUnitOrNonUnit diag, SCALAR alpha, ElConstDistMatrix_##SUF A,                 \
+                             ElDistMatrix_##SUF B);                                                         \
     /* factor / solve */                                                                                    \
     ElError ElCholeskyDist_##SUF(ElUpperOrLower uplo, ElDistMatrix_##SUF A);                                \
     ElError ElCholeskySolveAfterDist_##SUF(ElUpperOrLower uplo, ElOrientation orientation,                  \
@@ -157,6 +167,15 @@ ELB200_DECLARE_TYPE(s, float, float)
 ELB200_DECLARE_TYPE(d, double, double)
 ELB200_DECLARE_TYPE(c, elb200_c32, float)
 ELB200_DECLARE_TYPE(z, elb200_c64, double)
+/* Hermitian forms exist for the complex types only (include/El/blas_like/level3.h:109-112 Hemm, :163-166 Her2k) */
+#define ELB200_DECLARE_HERMITIAN(SUF, SCALAR, REAL)                                                         \
+    ElError ElHemmDist_##SUF(ElLeftOrRight side, ElUpperOrLower uplo, SCALAR alpha, ElConstDistMatrix_##SUF A, \
+                             ElConstDistMatrix_##SUF B, SCALAR beta, ElDistMatrix_##SUF C);                 \
+    ElError ElHer2kDist_##SUF(ElUpperOrLower uplo, ElOrientation orientation, SCALAR alpha,                 \
+                              ElConstDistMatrix_##SUF A, ElConstDistMatrix_##SUF B, REAL beta,              \
+                              ElDistMatrix_##SUF C);
+ELB200_DECLARE_HERMITIAN(c, elb200_c32, float)
+ELB200_DECLARE_HERMITIAN(z, elb200_c64, double)
 
 #ifdef __cplusplus
 }

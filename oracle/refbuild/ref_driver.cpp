@@ -128,6 +128,48 @@ int trrk(char uplo, char oA, char oB, int n, int k, T alpha, const T* A, int lda
         El::PopBlocksizeStack();
     });
 }
+// ---- the level-3 siblings SURVEY.md section 8f ranks next (they funnel into the same leaves) ----
+template <class T>
+int syr2k(char uplo, char o, int n, int k, T alpha, const T* A, int lda, const T* B, int ldb, T beta, T* C,
+          int ldc, int conjugate, int nb) {
+    return guarded([&] {
+        El::PushBlocksizeStack(nb);
+        El::DistMatrix<T> dA, dB, dC;
+        const bool tr = (o != 'N' && o != 'n');
+        lattach(dA, tr ? k : n, tr ? n : k, A, lda);
+        lattach(dB, tr ? k : n, tr ? n : k, B, ldb);
+        attach(dC, n, n, C, ldc);
+        El::Syr2k(ul(uplo), orient(o), alpha, dA, dB, beta, dC, conjugate != 0);
+        El::PopBlocksizeStack();
+    });
+}
+template <class T>
+int symm(char side, char uplo, int m, int n, T alpha, const T* A, int lda, const T* B, int ldb, T beta, T* C,
+         int ldc, int conjugate, int nb) {
+    return guarded([&] {
+        El::PushBlocksizeStack(nb);
+        El::DistMatrix<T> dA, dB, dC;
+        const int ka = (side == 'L' || side == 'l') ? m : n;
+        lattach(dA, ka, ka, A, lda);
+        lattach(dB, m, n, B, ldb);
+        attach(dC, m, n, C, ldc);
+        El::Symm(lr(side), ul(uplo), alpha, dA, dB, beta, dC, conjugate != 0);
+        El::PopBlocksizeStack();
+    });
+}
+template <class T>
+int trmm(char side, char uplo, char o, char diag, int m, int n, T alpha, const T* A, int lda, T* B, int ldb,
+         int nb) {
+    return guarded([&] {
+        El::PushBlocksizeStack(nb);
+        El::DistMatrix<T> dA, dB;
+        const int ka = (side == 'L' || side == 'l') ? m : n;
+        lattach(dA, ka, ka, A, lda);
+        attach(dB, m, n, B, ldb);
+        El::Trmm(lr(side), ul(uplo), orient(o), un(diag), alpha, dA, dB);
+        El::PopBlocksizeStack();
+    });
+}
 typedef El::Complex<double> Z;
 typedef El::Complex<float> Cf;
 }  // namespace
@@ -160,4 +202,11 @@ int elref_herk_d(char uplo, char o, int n, int k, double alpha, const double* A,
 int elref_herk_z(char uplo, char o, int n, int k, double alpha, const void* A, int lda, double beta, void* C, int ldc, int nb) { return herk<Z>(uplo, o, n, k, alpha, (const Z*)A, lda, beta, (Z*)C, ldc, nb); }
 
 int elref_trrk_d(char uplo, char oA, char oB, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb, double beta, double* C, int ldc, int nb) { return trrk<double>(uplo, oA, oB, n, k, alpha, A, lda, B, ldb, beta, C, ldc, nb); }
+
+int elref_syr2k_d(char uplo, char o, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb, double beta, double* C, int ldc, int conj, int nb) { return syr2k<double>(uplo, o, n, k, alpha, A, lda, B, ldb, beta, C, ldc, conj, nb); }
+int elref_syr2k_z(char uplo, char o, int n, int k, const double* alpha, const void* A, int lda, const void* B, int ldb, const double* beta, void* C, int ldc, int conj, int nb) { return syr2k<Z>(uplo, o, n, k, Z(alpha[0], alpha[1]), (const Z*)A, lda, (const Z*)B, ldb, Z(beta[0], beta[1]), (Z*)C, ldc, conj, nb); }
+int elref_symm_d(char side, char uplo, int m, int n, double alpha, const double* A, int lda, const double* B, int ldb, double beta, double* C, int ldc, int conj, int nb) { return symm<double>(side, uplo, m, n, alpha, A, lda, B, ldb, beta, C, ldc, conj, nb); }
+int elref_symm_z(char side, char uplo, int m, int n, const double* alpha, const void* A, int lda, const void* B, int ldb, const double* beta, void* C, int ldc, int conj, int nb) { return symm<Z>(side, uplo, m, n, Z(alpha[0], alpha[1]), (const Z*)A, lda, (const Z*)B, ldb, Z(beta[0], beta[1]), (Z*)C, ldc, conj, nb); }
+int elref_trmm_d(char side, char uplo, char o, char diag, int m, int n, double alpha, const double* A, int lda, double* B, int ldb, int nb) { return trmm<double>(side, uplo, o, diag, m, n, alpha, A, lda, B, ldb, nb); }
+int elref_trmm_z(char side, char uplo, char o, char diag, int m, int n, const double* alpha, const void* A, int lda, void* B, int ldb, int nb) { return trmm<Z>(side, uplo, o, diag, m, n, Z(alpha[0], alpha[1]), (const Z*)A, lda, (Z*)B, ldb, nb); }
 }

@@ -134,3 +134,44 @@ def trrk(uplo, oa, ob, alpha, A, B, beta, Cm, nb=128):
                             C.c_double(alpha), _p(A), A.shape[0], _p(B), B.shape[0], C.c_double(beta), _p(Cm), n,
                             int(nb)))
     return Cm
+
+
+# ---- siblings SURVEY.md section 8f ranks next (double and complex double) ----
+def syr2k(uplo, orient, alpha, A, B, beta, Cm, conjugate=False, nb=128):
+    """El::Syr2k / El::Her2k (conjugate=True) on the 1x1 grid, in place on the uplo triangle of Cm."""
+    assert Cm.flags.f_contiguous
+    dt = Cm.dtype
+    A, B = _f(A, dt), _f(B, dt)
+    n = Cm.shape[0]
+    k = A.shape[1] if orient.upper() == "N" else A.shape[0]
+    ka, av = _scalar(alpha, dt)
+    kb, bv = _scalar(beta, dt)
+    fn = getattr(lib(), "elref_syr2k_" + _SUF[dt])
+    _chk(fn(C.c_char(uplo.encode()), C.c_char(orient.encode()), n, k, av, _p(A), A.shape[0], _p(B), B.shape[0], bv,
+            _p(Cm), n, int(bool(conjugate)), int(nb)))
+    return Cm
+
+
+def symm(side, uplo, alpha, A, B, beta, Cm, conjugate=False, nb=128):
+    """El::Symm / El::Hemm (conjugate=True): only the uplo triangle of A is referenced."""
+    assert Cm.flags.f_contiguous
+    dt = Cm.dtype
+    A, B = _f(A, dt), _f(B, dt)
+    m, n = Cm.shape
+    ka, av = _scalar(alpha, dt)
+    kb, bv = _scalar(beta, dt)
+    fn = getattr(lib(), "elref_symm_" + _SUF[dt])
+    _chk(fn(C.c_char(side.encode()), C.c_char(uplo.encode()), m, n, av, _p(A), A.shape[0], _p(B), B.shape[0], bv,
+            _p(Cm), m, int(bool(conjugate)), int(nb)))
+    return Cm
+
+
+def trmm(side, uplo, orient, diag, alpha, A, B, nb=128):
+    """El::Trmm: B := alpha op(tri(A)) B (LEFT) or alpha B op(tri(A)) (RIGHT), in place."""
+    assert B.flags.f_contiguous
+    A = _f(A, B.dtype)
+    ka, av = _scalar(alpha, B.dtype)
+    fn = getattr(lib(), "elref_trmm_" + _SUF[B.dtype])
+    _chk(fn(C.c_char(side.encode()), C.c_char(uplo.encode()), C.c_char(orient.encode()), C.c_char(diag.encode()),
+            B.shape[0], B.shape[1], av, _p(A), A.shape[0], _p(B), B.shape[0], int(nb)))
+    return B

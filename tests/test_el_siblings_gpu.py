@@ -1,0 +1,110 @@
+"""GPU parity of the level-3 siblings SURVEY.md section 8f ranks next -- El::Syr2k / Her2k, Symm / Hemm, Trmm
+(elemental_b200/csrc/host/level3.cpp, compositions over Trrk / Gemm / the redistribution engine) -- against the
+reference library (or the numpy restatement that tests/test_oracle_cpu.py pins to it).
+
+NOT YET RUN ON A DEVICE: these entry points were written after the round's GPU budget was spent.  They are skipped
+unless ELB200_RUN_UNVERIFIED=1 so that the suite the driver runs only contains verified parity claims; the first
+GPU trip of the next round runs them (scripts/round2_first_trip.sh) and removes the gate.
+
+Tolerance: ||C - C_ref||_F <= 4 k eps ||A||_F ||B||_F as for Gemm; entries outside the triangle bit-identical."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import elemental_oracle as O
+from oracle import reference_lib as R
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("ELB200_RUN_UNVERIFIED") != "1",
+                                 reason="written without GPU access; set ELB200_RUN_UNVERIFIED=1 to run")]
+
+ORI = {"N": 0, "T": 1, "C": 2}
+UL = {"L": 0, "U": 1}
+LR = {"L": 0, "R": 1}
+DG = {"N": 0, "U": 1}
+
+
+@pytest.fixture(scope="module")
+def El():
+    from elemental_b200 import api
+    api.Initialize()
+    return api
+
+
+def _dm(El, a):
+    M = El.DistMatrix(a.dtype, 0, 2)
+    M.FromGlobal(a)
+    return M
+
+
+def _tol(k, dt, *mats):
+    e = np.finfo(np.dtype(dt).type(0).real.dtype).eps
+    prod = 1.0
+    for m in mats:
+        prod *= np.linalg.norm(m)
+    return 4 * k * e * prod
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128])
+def test_syr2k_her2k(El, dt):
+    n, k, nb = 150, 70, 32
+    alpha = 0.7 if dt == np.float64 else 0.7 - 0.3j
+    for conj in (False, True):
+        beta = 1.5 if (conj or dt == np.float64) else 1.5 + 0.25j
+        for uplo in "LU":
+            for orient in ("N", "C" if conj else "T"):
+                A = O.fill(0, *((n, k) if orient == "N" else (k, n)), 1, dtype=dt)
+                B = O.fill(0, *((n, k) if orient == "N" else (k, n)), 2, dtype=dt)
+                C0 = O.fill(0, n, n, 3, dtype=dt)
+                ref = (R.syr2k(uplo, orient, alpha, A, B, beta, C0.copy(order="F"), conjugate=conj, nb=nb)
+                       if R.available() else O.syr2k(uplo, orient, alpha, A, B, beta, C0.copy(order="F"), conjugate=conj))
+                dA, dB, dC = _dm(El, A), _dm(El, B), _dm(El, C0)
+                El.PushBlocksizeStack(nb)
+                (El.Her2k if conj else El.Syr2k)(UL[uplo], ORI[orient], alpha, dA, dB, beta, dC)
+                El.PopBlocksizeStack()
+                got = dC.ToGlobal()
+                mask = O._tri_mask(n, n, uplo)
+                assert np.array_equal(got[~mask], C0[~mask]), "the other triangle must not be touched"
+                assert np.linalg.norm((got - ref)[mask]) <= 2 * _tol(k, dt, A, B), (dt, conj, uplo, orient)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128])
+def test_symm_hemm(El, dt):
+    m, n, nb = 130, 90, 32
+    alpha, beta = (0.7, 1.5) if dt == np.float64 else (0.7 - 0.3j, 1.5 + 0.25j)
+    for conj in (False, True):
+        for side in "LR":
+            for uplo in "LU":
+                ka = m if side == "L" else n
+                A = O.fill(0, ka, ka, 1, dtype=dt)
+                if conj and dt == np.complex128:
+                    A[np.arange(ka), np.arange(ka)] = A[np.arange(ka), np.arange(ka)].real
+                B, C0 = O.fill(0, m, n, 2, dtype=dt), O.fill(0, m, n, 3, dtype=dt)
+                ref = (R.symm(side, uplo, alpha, A, B, beta, C0.copy(order="F"), conjugate=conj, nb=nb)
+                       if R.available() else O.symm(side, uplo, alpha, A, B, beta, C0.copy(order="F"), conjugate=conj))
+                dA, dB, dC = _dm(El, A), _dm(El, B), _dm(El, C0)
+                El.PushBlocksizeStack(nb)
+                (El.Hemm if conj else El.Symm)(LR[side], UL[uplo], alpha, dA, dB, beta, dC)
+                El.PopBlocksizeStack()
+                assert np.array_equal(dA.ToGlobal(), A), "A is read-only"
+                assert np.linalg.norm(dC.ToGlobal() - ref) <= _tol(ka, dt, A, B), (dt, conj, side, uplo)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128])
+def test_trmm(El, dt):
+    m, n, nb = 120, 75, 32
+    alpha = 0.7 if dt == np.float64 else 0.7 - 0.3j
+    for side in "LR":
+        for uplo in "LU":
+            for orient in "NTC":
+                for diag in "NU":
+                    ka = m if side == "L" else n
+                    A, B0 = O.fill(0, ka, ka, 1, dtype=dt), O.fill(0, m, n, 2, dtype=dt)
+                    ref = (R.trmm(side, uplo, orient, diag, alpha, A, B0.copy(order="F"), nb=nb)
+                           if R.available() else O.trmm(side, uplo, orient, diag, alpha, A, B0.copy(order="F")))
+                    dA, dB = _dm(El, A), _dm(El, B0)
+                    El.PushBlocksizeStack(nb)
+                    El.Trmm(LR[side], UL[uplo], ORI[orient], DG[diag], alpha, dA, dB)
+                    El.PopBlocksizeStack()
+                    assert np.linalg.norm(dB.ToGlobal() - ref) <= _tol(ka, dt, A, B0), (dt, side, uplo, orient, diag)
