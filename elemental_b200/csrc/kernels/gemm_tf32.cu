@@ -149,6 +149,21 @@ __device__ __forceinline__ unsigned make_idesc() {
            ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
 }
 
+// tile index -> (tile row, tile column): bands of RASTER_N tile columns walked down the rows, so the ~148
+// tiles in flight cover about 9 x 16 tiles and share 25 operand panels instead of the 66 of a plain
+// column-major walk (ncu of the first version: 49 GB of DRAM reads for 2.4 GB of operands).  Used by the
+// producer and the epilogue alike; exported for the CPU bijection test (elb200_tf32_tile_coords).
+constexpr int RASTER_N = 16;
+__host__ __device__ __forceinline__ void tf32_tile_coords(i64 t, i64 tilesM, i64 tilesN, i64& tm, i64& tn) {
+    const i64 band_sz = (i64)RASTER_N * tilesM;
+    const i64 band = t / band_sz;
+    const i64 first_n = band * RASTER_N;
+    const i64 bw = (tilesN - first_n < RASTER_N) ? (tilesN - first_n) : (i64)RASTER_N;
+    const i64 in_band = t - band * band_sz;
+    tm = in_band / bw;
+    tn = first_n + (in_band - tm * bw);
+}
+
 template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(NUM_THREADS, 1) sgemm_3xtf32_kernel(const __grid_constant__ TcArgs p) {
     extern __shared__ unsigned char smem_raw[];
@@ -194,7 +209,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sgemm_3xtf32_kernel(const __gr
             int stage = 0;
             unsigned ph = 0;
             for (i64 t = blockIdx.x; t < total; t += gridDim.x) {
-                const int m0 = (int)((t % p.tilesM) * BM), n0 = (int)((t / p.tilesM) * BN);
+                i64 tm, tn;
+                tf32_tile_coords(t, p.tilesM, p.tilesN, tm, tn);
+                const int m0 = (int)(tm * BM), n0 = (int)(tn * BN);
                 for (i64 kb = 0; kb < KB; ++kb) {
                     mbar_wait(empty0 + 8 * stage, ph ^ 1u);
                     const unsigned sa = base + stage * STAGE_BYTES, sb = sa + OP_BYTES;
@@ -292,7 +309,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sgemm_3xtf32_kernel(const __gr
         const float alpha = p.alpha, beta = p.beta;
         unsigned ci = 0;
         for (i64 t = blockIdx.x; t < total; t += gridDim.x) {
-            const i64 m0 = (t % p.tilesM) * BM, n0 = (t / p.tilesM) * BN + half * 64;
+            i64 tm, tn;
+            tf32_tile_coords(t, p.tilesM, p.tilesN, tm, tn);
+            const i64 m0 = tm * BM, n0 = tn * BN + half * 64;
             float sum[64];
             for (i64 kb0 = 0; kb0 < KB; kb0 += KCHUNK, ++ci) {
                 const unsigned acc = ci & 1u, aph = (ci >> 1) & 1u;
@@ -470,6 +489,11 @@ int elb200_sgemm_3xtf32(char ta, char tb, int64_t m, int64_t n, int64_t k, float
                 "sgemm_3xtf32: operands must be 16-byte aligned with leading dimensions that are multiples of 4 "
                 "(TMA); use elb200_sgemm for arbitrary layouts");
     });
+}
+void elb200_tf32_tile_coords(int64_t t, int64_t tilesM, int64_t tilesN, int64_t* tm, int64_t* tn) {
+    i64 a = 0, b = 0;
+    elb200::tf32_tile_coords(t, tilesM, tilesN, a, b);
+    *tm = a; *tn = b;
 }
 void elb200_sgemm_set_mode(int mode) { elb200::g_sgemm_mode = mode == 1 ? 1 : 0; }
 int elb200_sgemm_get_mode(void) { return elb200::g_sgemm_mode; }

@@ -86,6 +86,8 @@ int elb200_cgemm(char transA, char transB, int64_t m, int64_t n, int64_t k,
                  elb200_c32 beta, elb200_c32* C, int64_t ldc, elb200_stream_t s);
 /* float GEMM on tcgen05 (kind::tf32) with the 3xTF32 operand split;
  * relative error per product ~2^-21 instead of 2^-24 */
+/* the 3xTF32 kernel's tile rasterisation (host copy of the device function; tests check it is a bijection) */
+void elb200_tf32_tile_coords(int64_t tile, int64_t tilesM, int64_t tilesN, int64_t* tileRow, int64_t* tileCol);
 int elb200_sgemm_3xtf32(char transA, char transB, int64_t m, int64_t n, int64_t k,
                  float alpha, const float* A, int64_t lda,
                  const float* B, int64_t ldb,

@@ -92,3 +92,26 @@ def test_gemm_selector_matches_reference_rule():
         assert L.elb200_gemm_default_algorithm(C.c_int64(m), C.c_int64(n), C.c_int64(k)) == O.gemm_select(m, n, k)
     assert L.elb200_gemm_default_algorithm(C.c_int64(8192), C.c_int64(8192), C.c_int64(262144)) == O.GEMM_SUMMA_DOT
     assert L.elb200_gemm_default_algorithm(C.c_int64(32768), C.c_int64(32768), C.c_int64(32768)) == O.GEMM_SUMMA_C
+
+
+def test_tf32_tile_raster_is_a_bijection():
+    """The 3xTF32 kernel's producer and epilogue warps map a linear tile index to (tile row, tile column) with
+    elb200_tf32_tile_coords (host copy of the device function): every tile exactly once, ragged last band included."""
+    import ctypes as C
+    from elemental_b200._lib import lib
+    L = lib()
+    L.elb200_tf32_tile_coords.restype = None
+    tm, tn = C.c_int64(), C.c_int64()
+    for tilesM, tilesN in [(1, 1), (1, 40), (40, 1), (7, 16), (7, 17), (64, 64), (16, 31), (3, 33), (5, 48)]:
+        seen = set()
+        for t in range(tilesM * tilesN):
+            L.elb200_tf32_tile_coords(C.c_int64(t), C.c_int64(tilesM), C.c_int64(tilesN), C.byref(tm), C.byref(tn))
+            assert 0 <= tm.value < tilesM and 0 <= tn.value < tilesN, (tilesM, tilesN, t, tm.value, tn.value)
+            seen.add((tm.value, tn.value))
+        assert len(seen) == tilesM * tilesN, (tilesM, tilesN)
+    # consecutive tiles stay within a band of 16 tile columns (the L2 reuse the raster is for)
+    cols = set()
+    for t in range(148):
+        L.elb200_tf32_tile_coords(C.c_int64(t), C.c_int64(64), C.c_int64(64), C.byref(tm), C.byref(tn))
+        cols.add(tn.value)
+    assert len(cols) <= 16
