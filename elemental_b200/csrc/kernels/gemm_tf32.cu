@@ -14,7 +14,7 @@
 // TMEM -- the same order as an FFMA chain of length k (tests state the tolerance against an FP64
 // product).
 //
-// Structure (one persistent CTA per SM, 320 threads, 128 x 128 C tiles, k-blocks of 32):
+// Structure (one persistent CTA per SM, 448 threads, 128 x 128 C tiles, k-blocks of 32):
 //   warp 0      TMA producer: cp.async.bulk.tensor.2d (128-byte swizzle) of the raw fp32 A and B
 //               k-blocks into a 3-stage ring, completion on an mbarrier;
 //   warps 2-5   splitters: read the landed fp32 block, write hi in place and lo into a second
@@ -32,9 +32,10 @@
 // chunk accumulates in TMEM, the epilogue warps promote it into registers with round-to-nearest
 // adds (the two TMEM accumulators alternate between chunks), so the drift is bounded by the chunk
 // length whatever k is.
-// Operands may be K-major (A 'T', B 'N': k contiguous) or MN-major (A 'N', B 'T'): both are
-// canonical UMMA layouts of the 128-byte swizzle; only the TMA boxes and the descriptor strides
-// differ.  TMA zero-fills ragged m / n / k edges.
+// Operands may be K-major (A 'T', B 'N': k contiguous; plain 128-byte swizzle) or MN-major (A 'N',
+// B 'T'; the 32-byte-atom flavour of the 128-byte swizzle, the only layout from which the tensor
+// core transposes 32-bit operands -- see make_desc): TMA boxes, swizzle mode and descriptor differ.
+// TMA zero-fills ragged m / n / k edges.
 //
 // Requirements: A, B 16-byte aligned, lda, ldb multiples of 4 (TMA strides are multiples of 16 B).
 #include <cuda.h>
