@@ -86,7 +86,7 @@ struct TmaArgs {
     i64 tilesM, tilesN;
     int flags;  // tuning/debug: bit0 = stagger the two groups, bit1 = always use the masked epilogue,
                 // bit2 = only group 0 works, bit3 = 4 warps per group (warp tile 64 x 32) instead of 8,
-                // bit4 = never use the L2 reduction epilogue, bit5 / bit6 = one-off start offsets per SM / per group
+                // bit4 = never use the L2 reduction epilogue, bit7 / bit8 = diagnostic kernels (MODE 3 / 4, NN only), bit5 / bit6 = one-off start offsets per SM / per group
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -169,7 +169,7 @@ __device__ __forceinline__ void tile_coords(const TmaArgs& p, i64 tile64, i64& t
 
 template <int MODE>
 __device__ __forceinline__ bool tile_active(const TmaArgs& p, i64 tm, i64 tn) {
-    if (MODE == 0) return true;
+    if (MODE == 0 || MODE >= 3) return true;
     const i64 m0 = tm * TM, n0 = tn * TN;
     const i64 mlast = (m0 + TM - 1 < p.m - 1) ? (m0 + TM - 1) : (p.m - 1);
     const i64 nlast = (n0 + TN - 1 < p.n - 1) ? (n0 + TN - 1) : (p.n - 1);
@@ -197,7 +197,10 @@ __device__ __forceinline__ void issue_stage(const TmaArgs& p, unsigned sa, unsig
     }
 }
 
-// MODE 0: full GEMM; 1: lower-triangle TRRK; 2: upper-triangle TRRK
+// MODE 0: full GEMM; 1: lower-triangle TRRK; 2: upper-triangle TRRK;
+// 3 / 4: DIAGNOSTIC full GEMM whose interior tiles skip the C update / use plain stores C = alpha acc (wrong
+// results on purpose: they split the rank-nb deficit between the pipeline and the epilogue; separate
+// instantiations, so the code generated for modes 0-2 is untouched)
 template <class CF, bool A_KMAJOR, bool B_KMAJOR, int MODE>
 __global__ void __launch_bounds__(CF::NTHREADS, 1) gemm_f64_tma_kernel(const __grid_constant__ TmaArgs p) {
     constexpr int CONSUMER_WARPS = CF::WARPS, FM = CF::FM, FN = CF::FN;
@@ -394,7 +397,23 @@ __global__ void __launch_bounds__(CF::NTHREADS, 1) gemm_f64_tma_kernel(const __g
             // fast path (all but the edge / diagonal tiles): no masks, one base pointer per column
             // and compile-time row offsets; two memory round trips per tile
             double* cbase = p.C + (m0 + wm0 + tile_row<A_KMAJOR>(0, g)) + (n0 + wn0) * p.ldc;
-            if (useRed) {
+            if constexpr (MODE == 3) {
+                double sink = 0.0;   // keeps the accumulators alive
+#pragma unroll
+                for (int i = 0; i < FM; ++i)
+#pragma unroll
+                    for (int j = 0; j < FN; ++j) sink += acc[i][j][0] + acc[i][j][1];
+                if (sink == 1.2345e300) cbase[0] = sink;
+            } else if constexpr (MODE == 4) {
+#pragma unroll
+                for (int j = 0; j < FN; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        double* cptr = cbase + (i64)tile_row<B_KMAJOR>(j, 2 * t + e) * p.ldc;
+#pragma unroll
+                        for (int i = 0; i < FM; ++i) cptr[tile_row<A_KMAJOR>(i, 0)] = __dmul_rn(alpha, acc[i][j][e]);
+                    }
+            } else if (useRed) {
 #pragma unroll
                 for (int j = 0; j < FN; ++j)
 #pragma unroll
@@ -565,6 +584,11 @@ bool dgemm_tma_device(int mode, bool ta, bool tb, i64 m, i64 n, i64 k, double al
     a.tilesM = ceil_div(m, TM);
     a.tilesN = ceil_div(n, TN);
     a.flags = g_dgemm_tma_flags;
+    if (mode == 0 && (a.flags & 384) && !ak && bk) {   // diagnostic epilogues, NN only
+        if (a.flags & 128) launch<Cfg8, false, true, 3>(a, flops, s);
+        else launch<Cfg8, false, true, 4>(a, flops, s);
+        return true;
+    }
     if (mode == 0) dispatch<0>(ak, bk, a, flops, s);
     else if (mode == 1) dispatch<1>(ak, bk, a, flops, s);
     else dispatch<2>(ak, bk, a, flops, s);
