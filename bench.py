@@ -240,6 +240,8 @@ def main():
         pass
     flops_step = 2.0 * n ** 3
     value = flops_step * args.steps / (ms * 1e-3) / 1e9
+    kernel_tf = kflops.value / (kms.value * 1e-3) / 1e12 if kms.value > 0 else 0.0
+
     # ---- DPOTRF (BASELINE.json configs[2]) ----
     potrf = None
     if not args.no_potrf:
