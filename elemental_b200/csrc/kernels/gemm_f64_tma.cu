@@ -86,7 +86,7 @@ struct TmaArgs {
     i64 tilesM, tilesN;
     int flags;  // tuning/debug: bit0 = stagger the two groups, bit1 = always use the masked epilogue,
                 // bit2 = only group 0 works, bit3 = 4 warps per group (warp tile 64 x 32) instead of 8,
-                // bit4 = never use the L2 reduction epilogue, bit7 / bit8 = diagnostic kernels (MODE 3 / 4, NN only), bit5 / bit6 = one-off start offsets per SM / per group
+                // bit4 = never use the L2 reduction epilogue, bit7 / bit8 = diagnostic kernels (MODE 3 / 4, NN only), bit9 = fragment-prefetch kernel (MODE 5, NN only), bit5 / bit6 = one-off start offsets per SM / per group
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -200,7 +200,8 @@ __device__ __forceinline__ void issue_stage(const TmaArgs& p, unsigned sa, unsig
 // MODE 0: full GEMM; 1: lower-triangle TRRK; 2: upper-triangle TRRK;
 // 3 / 4: DIAGNOSTIC full GEMM whose interior tiles skip the C update / use plain stores C = alpha acc (wrong
 // results on purpose: they split the rank-nb deficit between the pipeline and the epilogue; separate
-// instantiations, so the code generated for modes 0-2 is untouched)
+// instantiations, so the code generated for modes 0-2 is untouched); 5: EXPERIMENT, full GEMM whose
+// fragment loads run one k-step ahead of the DMMAs (bit-identical results)
 template <class CF, bool A_KMAJOR, bool B_KMAJOR, int MODE>
 __global__ void __launch_bounds__(CF::NTHREADS, 1) gemm_f64_tma_kernel(const __grid_constant__ TmaArgs p) {
     constexpr int CONSUMER_WARPS = CF::WARPS, FM = CF::FM, FN = CF::FN;
@@ -355,6 +356,57 @@ __global__ void __launch_bounds__(CF::NTHREADS, 1) gemm_f64_tma_kernel(const __g
             mbar_wait(go_bar, 0);
             released = true;
         }
+        if constexpr (MODE == 5) {
+            // EXPERIMENT (separate instantiation, elb200_dgemm_set_debug_flags(512), NN only): the fragments of
+            // k-step ks + 1 are loaded before the DMMAs of k-step ks are issued -- across k-stage boundaries
+            // too -- so a fragment load may sit behind a burst of the other group's epilogue REDs in the LSU
+            // queue for a whole k-step (~1000 clocks) without starving the tensor pipe.  Same DMMA order as the
+            // default loop, hence bit-identical results.
+            double fa[2][FM], fb[2][FN];
+            auto load_frags = [&](double (&a)[FM], double (&b)[FN], unsigned sa, unsigned sb, int ks) {
+#pragma unroll
+                for (int i = 0; i < FM; ++i) {
+                    if (A_KMAJOR) a[i] = lds64(sa + aoff[ks] + (unsigned)i * 1024u);
+                    else a[i] = lds64(sa + aoff[(i & 1) + 2 * (ks & 1)] + (unsigned)(i >> 1) * 2048u + (unsigned)ks * 512u);
+                }
+#pragma unroll
+                for (int j = 0; j < FN; ++j) {
+                    if (B_KMAJOR) b[j] = lds64(sb + boff[ks] + (unsigned)j * 1024u);
+                    else b[j] = lds64(sb + boff[(j & 1) + 2 * (ks & 1)] + (unsigned)(j >> 1) * 2048u + (unsigned)ks * 512u);
+                }
+            };
+#pragma unroll 1
+            for (i64 kt = 0; kt < KT; ++kt) {
+                if (cw == 0) producer_step();
+                const unsigned sa = ring + stage * STAGE_BYTES;
+                const unsigned sb = sa + A_BYTES;
+                if (kt == 0) {
+                    mbar_wait(full0 + stage * 8, phase);
+                    load_frags(fa[0], fb[0], sa, sb, 0);
+                }
+                const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
+                const unsigned nphase = (stage + 1 == STAGES) ? (phase ^ 1u) : phase;
+#pragma unroll
+                for (int ks = 0; ks < BK / 4; ++ks) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int cur = ks & 1;
+                    if (ks + 1 < BK / 4) {
+                        load_frags(fa[cur ^ 1], fb[cur ^ 1], sa, sb, ks + 1);
+                    } else if (kt + 1 < KT) {
+                        mbar_wait(full0 + nstage * 8, nphase);
+                        const unsigned na = ring + nstage * STAGE_BYTES;
+                        load_frags(fa[cur ^ 1], fb[cur ^ 1], na, na + A_BYTES, 0);
+                    }
+#pragma unroll
+                    for (int i = 0; i < FM; ++i)
+#pragma unroll
+                        for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[cur][i], fb[cur][j]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + stage * 8);
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        } else
 #pragma unroll 1
         for (i64 kt = 0; kt < KT; ++kt) {
             if (stagger && group == 0 && !released && 2 * kt + 1 >= KT) {
@@ -587,6 +639,10 @@ bool dgemm_tma_device(int mode, bool ta, bool tb, i64 m, i64 n, i64 k, double al
     if (mode == 0 && (a.flags & 384) && !ak && bk) {   // diagnostic epilogues, NN only
         if (a.flags & 128) launch<Cfg8, false, true, 3>(a, flops, s);
         else launch<Cfg8, false, true, 4>(a, flops, s);
+        return true;
+    }
+    if (mode == 0 && (a.flags & 512) && !ak && bk) {   // experiment: fragment prefetch one k-step ahead, NN only
+        launch<Cfg8, false, true, 5>(a, flops, s);
         return true;
     }
     if (mode == 0) dispatch<0>(ak, bk, a, flops, s);

@@ -1,6 +1,6 @@
 """TMA DGEMM kernel under debug flag combinations: bit0 stagger the groups, bit1 masked epilogue everywhere, bit2 one group only,
-bit4 no L2-reduction epilogue, bit5/6 start offsets per SM / group, bit7 NO C update (diagnostic), bit8 plain stores (diagnostic).
-usage: python scripts/gpu_dgemm_flags.py 0 128 256 16"""
+bit4 no L2-reduction epilogue, bit5/6 start offsets per SM / group, bit7 NO C update (diagnostic), bit8 plain stores (diagnostic), bit9 fragment prefetch one k-step ahead (experiment).
+usage: python scripts/gpu_dgemm_flags.py 0 128 256 512 16"""
 import ctypes as C, sys
 import torch
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
