@@ -21,6 +21,7 @@
 // packed once.  When the source is replicated, the destination pulls from the replica
 // in its own grid row / column, which makes every "filter" redistribution purely local.
 #include <algorithm>
+#include <cmath>
 #include <map>
 #include <tuple>
 
@@ -438,9 +439,9 @@ void HashFill(AbstractDistMatrix<T>& A, int kind, uint64_t seed, double diag) {
 }
 
 namespace {
-// reduce a device double over the ranks that hold DISTINCT pieces of A
+// the communicator over which the ranks hold DISTINCT pieces of A (null: every rank holds all of it)
 template <typename T>
-double ReduceOverOwners(const AbstractDistMatrix<T>& A, double* dval, ncclRedOp_t op) {
+const Comm* OwnersComm(const AbstractDistMatrix<T>& A) {
     const Grid& g = A.Grid();
     const bool pinsI = PinsRow(A.ColDist()) || PinsRow(A.RowDist());
     const bool pinsJ = PinsCol(A.ColDist()) || PinsCol(A.RowDist());
@@ -448,34 +449,54 @@ double ReduceOverOwners(const AbstractDistMatrix<T>& A, double* dval, ncclRedOp_
     if (pinsI && pinsJ) comm = &g.VCComm();
     else if (pinsI) comm = &g.MCComm();
     else if (pinsJ) comm = &g.MRComm();
-    if (comm && comm->size > 1)
-        ELB_NCCL(ncclAllReduce(dval, dval, 1, ncclDouble, op, (ncclComm_t)comm->nccl, dev::stream()));
+    return (comm && comm->size > 1) ? comm : nullptr;
+}
+double ReadDeviceDouble(const double* d) {
     double out = 0.0;
-    ELB_CUDA(cudaMemcpyAsync(&out, dval, sizeof(double), cudaMemcpyDeviceToHost, dev::stream()));
+    ELB_CUDA(cudaMemcpyAsync(&out, d, sizeof(double), cudaMemcpyDeviceToHost, dev::stream()));
     ELB_CUDA(cudaStreamSynchronize(dev::stream()));
     return out;
 }
-}  // namespace
-
+// max |a_ij| over the whole matrix into d[0].  The reduction across ranks runs on the BIT PATTERN
+// (non-negative doubles order like unsigned integers, +inf and the canonical NaN on top), so a NaN
+// on any rank reaches every rank whatever NCCL's floating-point max does with NaNs.
 template <typename T>
-Base<T> FrobeniusNorm(const AbstractDistMatrix<T>& A) {
-    double* d = (double*)elb200::scratch_alloc(sizeof(double), dev::stream());
-    ELB_CUDA(cudaMemsetAsync(d, 0, sizeof(double), dev::stream()));
-    dev::c_check(elb200_sumsq(dev::Code<T>(), A.LocalHeight(), A.LocalWidth(), A.LockedBuffer(), A.LDim(), d,
-                              (elb200_stream_t)dev::stream()),
-                 "elb200_sumsq");
-    const double s = ReduceOverOwners(A, d, ncclSum);
-    elb200::scratch_free(d, dev::stream());
-    return (Base<T>)std::sqrt(s);
-}
-template <typename T>
-Base<T> MaxNorm(const AbstractDistMatrix<T>& A) {
-    double* d = (double*)elb200::scratch_alloc(sizeof(double), dev::stream());
+void DeviceMaxAbs(const AbstractDistMatrix<T>& A, double* d) {
     ELB_CUDA(cudaMemsetAsync(d, 0, sizeof(double), dev::stream()));
     dev::c_check(elb200_maxabs(dev::Code<T>(), A.LocalHeight(), A.LocalWidth(), A.LockedBuffer(), A.LDim(), d,
                                (elb200_stream_t)dev::stream()),
                  "elb200_maxabs");
-    const double s = ReduceOverOwners(A, d, ncclMax);
+    if (const Comm* comm = OwnersComm(A))
+        ELB_NCCL(ncclAllReduce(d, d, 1, ncclUint64, ncclMax, (ncclComm_t)comm->nccl, dev::stream()));
+}
+}  // namespace
+
+// Two passes, both on the device: the max-abs, then the sum of squares of the entries divided by it
+// (src/lapack_like/props/Norm/Frobenius.cpp keeps the same (scale, scaledSquare) pair in one host
+// pass): no overflow for |a| > 1e154, no underflow for tiny entries, NaN / inf propagate.
+template <typename T>
+Base<T> FrobeniusNorm(const AbstractDistMatrix<T>& A) {
+    double* d = (double*)elb200::scratch_alloc(2 * sizeof(double), dev::stream());
+    ELB_CUDA(cudaMemsetAsync(d, 0, 2 * sizeof(double), dev::stream()));
+    DeviceMaxAbs(A, d);
+    dev::c_check(elb200_sumsq_scaled(dev::Code<T>(), A.LocalHeight(), A.LocalWidth(), A.LockedBuffer(), A.LDim(), d,
+                                     d + 1, (elb200_stream_t)dev::stream()),
+                 "elb200_sumsq_scaled");
+    if (const Comm* comm = OwnersComm(A))
+        ELB_NCCL(ncclAllReduce(d + 1, d + 1, 1, ncclDouble, ncclSum, (ncclComm_t)comm->nccl, dev::stream()));
+    double h[2] = {0.0, 0.0};
+    ELB_CUDA(cudaMemcpyAsync(h, d, 2 * sizeof(double), cudaMemcpyDeviceToHost, dev::stream()));
+    ELB_CUDA(cudaStreamSynchronize(dev::stream()));
+    elb200::scratch_free(d, dev::stream());
+    const double scale = h[0];
+    if (!(scale > 0.0) || !(scale < HUGE_VAL)) return (Base<T>)scale;  // 0, inf or NaN
+    return (Base<T>)(scale * std::sqrt(h[1]));
+}
+template <typename T>
+Base<T> MaxNorm(const AbstractDistMatrix<T>& A) {
+    double* d = (double*)elb200::scratch_alloc(sizeof(double), dev::stream());
+    DeviceMaxAbs(A, d);
+    const double s = ReadDeviceDouble(d);
     elb200::scratch_free(d, dev::stream());
     return (Base<T>)s;
 }

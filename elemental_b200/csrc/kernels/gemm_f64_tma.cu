@@ -42,6 +42,7 @@
 
 namespace elb200 {
 int g_dgemm_tma_flags = 0;
+unsigned long long* g_dgemm_tma_prof = nullptr;
 namespace {
 
 constexpr int BK = 16;             // doubles per k-stage = one 128-byte swizzle span
@@ -84,6 +85,7 @@ struct TmaArgs {
     double alpha, beta;
     i64 gi0, gis, gj0, gjs;
     i64 tilesM, tilesN;
+    unsigned long long* prof;  // MODE 6 only: per-warp clock counters, 8 per warp
     int flags;  // tuning/debug: bit0 = stagger the two groups, bit1 = always use the masked epilogue,
                 // bit2 = only group 0 works, bit3 = 4 warps per group (warp tile 64 x 32) instead of 8,
                 // bit4 = never use the L2 reduction epilogue, bit7 / bit8 = diagnostic kernels (MODE 3 / 4, NN only), bit9 = fragment-prefetch kernel (MODE 5, NN only), bit5 / bit6 = one-off start offsets per SM / per group
@@ -327,13 +329,19 @@ __global__ void __launch_bounds__(CF::NTHREADS, 1) gemm_f64_tma_kernel(const __g
     };
     if (cw == 0) {
         producer_seek(first_tile);
+        const int lookahead = (p.flags & 2048) ? LOOKAHEAD - 1 : LOOKAHEAD;  // bit 11: producer 2 stages ahead
 #pragma unroll 1
-        for (int i = 0; i < LOOKAHEAD; ++i) producer_step();
+        for (int i = 0; i < lookahead; ++i) producer_step();
     }
 
     int stage = 0;
     unsigned phase = 0;
     const double alpha = p.alpha, beta = p.beta;
+    // MODE 6 (diagnostic instantiation): SM clocks this warp spent in {0 producer_step, 1 waiting for a full
+    // stage, 2 fragment loads + DMMAs, 3 epilogue, 4 whole kernel, 5 tiles}
+    long long pc[6] = {0, 0, 0, 0, 0, 0};
+    long long pt0 = 0, ptk = 0;
+    if constexpr (MODE == 6) pt0 = clock64();
     // Optional stagger (flags bit 0): group 1 starts its first tile when group 0 is half-way
     // through its own, so that the epilogue of one group runs under the main loop of the other.
     const unsigned go_bar = bars + GO_BAR_OFFSET;
@@ -414,8 +422,11 @@ __global__ void __launch_bounds__(CF::NTHREADS, 1) gemm_f64_tma_kernel(const __g
                 if (lane == 0) mbar_arrive(go_bar);
                 released = true;
             }
+            if constexpr (MODE == 6) ptk = clock64();
             if (cw == 0) producer_step();
+            if constexpr (MODE == 6) { const long long t = clock64(); pc[0] += t - ptk; ptk = t; }
             mbar_wait(full0 + stage * 8, phase);
+            if constexpr (MODE == 6) { const long long t = clock64(); pc[1] += t - ptk; ptk = t; }
             const unsigned sa = ring + stage * STAGE_BYTES;
             const unsigned sb = sa + A_BYTES;
 #pragma unroll
@@ -439,7 +450,9 @@ __global__ void __launch_bounds__(CF::NTHREADS, 1) gemm_f64_tma_kernel(const __g
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + stage * 8);
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            if constexpr (MODE == 6) pc[2] += clock64() - ptk;
         }
+        if constexpr (MODE == 6) { ptk = clock64(); pc[5] += 1; }
 
         // ---- epilogue: C = alpha*acc + beta*C; C was prefetched into L2 by the producer ----
         bool interior = (m0 + TM <= p.m) && (n0 + TN <= p.n);
@@ -537,6 +550,14 @@ __global__ void __launch_bounds__(CF::NTHREADS, 1) gemm_f64_tma_kernel(const __g
                     }
                 }
             }
+        }
+        if constexpr (MODE == 6) pc[3] += clock64() - ptk;
+    }
+    if constexpr (MODE == 6) {
+        pc[4] = clock64() - pt0;
+        if (lane == 0 && p.prof) {
+            unsigned long long* out = p.prof + ((size_t)blockIdx.x * (GROUPS * CONSUMER_WARPS) + warp) * 8;
+            for (int i = 0; i < 6; ++i) out[i] = (unsigned long long)pc[i];
         }
     }
     // a group that never ran a tile must still release the other one
@@ -636,6 +657,11 @@ bool dgemm_tma_device(int mode, bool ta, bool tb, i64 m, i64 n, i64 k, double al
     a.tilesM = ceil_div(m, TM);
     a.tilesN = ceil_div(n, TN);
     a.flags = g_dgemm_tma_flags;
+    a.prof = g_dgemm_tma_prof;
+    if (mode == 0 && (a.flags & 1024) && !ak && bk) {  // diagnostic: per-warp phase clocks, NN only
+        launch<Cfg8, false, true, 6>(a, flops, s);
+        return true;
+    }
     if (mode == 0 && (a.flags & 384) && !ak && bk) {   // diagnostic epilogues, NN only
         if (a.flags & 128) launch<Cfg8, false, true, 3>(a, flops, s);
         else launch<Cfg8, false, true, 4>(a, flops, s);
@@ -653,4 +679,10 @@ bool dgemm_tma_device(int mode, bool ta, bool tb, i64 m, i64 n, i64 k, double al
 
 }  // namespace elb200
 
-extern "C" void elb200_dgemm_set_debug_flags(int f) { elb200::g_dgemm_tma_flags = f; }
+namespace elb200 { extern int g_dgemm_ws_flags; extern unsigned long long* g_dgemm_ws_prof; }
+extern "C" void elb200_dgemm_set_debug_flags(int f) { elb200::g_dgemm_tma_flags = f; elb200::g_dgemm_ws_flags = f; }
+// device buffer of (grid * 16 warps * 8) u64 for the phase-clock diagnostic (flags bit 10)
+extern "C" void elb200_dgemm_set_profile_buffer(void* p) {
+    elb200::g_dgemm_tma_prof = (unsigned long long*)p;
+    elb200::g_dgemm_ws_prof = (unsigned long long*)p;
+}

@@ -69,11 +69,12 @@ void lattice_copy_t(const elb200_lattice* descs, int ndesc, int conj, const void
         has_alpha = scalar_traits<T>::is_one(a) ? 0 : 1;
     }
     const int cap = sm_count() * 8;
-    for (int base = 0; base < ndesc; base += MAX_BATCH) {
+    int i = 0;  // scan index: every batch resumes where the previous one stopped (empty descriptors are skipped)
+    while (i < ndesc) {
         LatticeBatch b;
         b.n = 0;
         i64 maxtiles = 0;
-        for (int i = base; i < ndesc && b.n < MAX_BATCH; ++i) {
+        for (; i < ndesc && b.n < MAX_BATCH; ++i) {
             if (descs[i].nrows <= 0 || descs[i].ncols <= 0) continue;
             b.d[b.n++] = descs[i];
             i64 t = ceil_div(descs[i].nrows, 32) * ceil_div(descs[i].ncols, 32);
@@ -180,26 +181,44 @@ void fill_hash_t(int kind, i64 m, i64 n, void* A, i64 lda, i64 gi0, i64 gis, i64
 }
 
 __device__ inline void atomic_max_nonneg(double* addr, double v) {
-    // valid for non-negative doubles: their bit patterns order like integers
+    // valid for non-negative doubles: their bit patterns order like integers, +inf above every finite
+    // value and the canonical quiet NaN above +inf, so a NaN anywhere survives the reduction
+    if (v != v) v = __longlong_as_double(0x7ff8000000000000LL);
     atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
 }
+template <class T> __device__ inline double abs_entry(T x) { return fabs((double)x); }
+template <> __device__ inline double abs_entry<c32_t>(c32_t x) { return hypot((double)x.re, (double)x.im); }
+template <> __device__ inline double abs_entry<c64_t>(c64_t x) { return hypot(x.re, x.im); }
+// NaN-propagating max: a NaN operand wins and is never dropped again
+__device__ inline double nanmax(double acc, double v) { return (v > acc || v != v) ? v : acc; }
 
-// MODE 0: sum of squares; MODE 1: max abs
+// MODE 0: sum of |a_ij / scale|^2 (scale read from device memory, 1 when the pointer is null or the
+// value is 0 / not finite); MODE 1: max |a_ij|, NaN-propagating.  Together they give the scaled
+// two-pass Frobenius norm max * sqrt(sum |a/max|^2), which neither overflows nor underflows
+// (the reference's UpdateScaledSquare does the same in one pass).
 template <class T, int MODE>
 __global__ void __launch_bounds__(256) reduce_kernel(i64 m, i64 n, const T* __restrict__ A, i64 lda,
-                                                     double* out) {
+                                                     const double* __restrict__ scale_dev, double* out) {
     double acc = 0.0;
+    double inv = 1.0;
+    if (MODE == 0 && scale_dev) {
+        const double sc = *scale_dev;
+        if (sc > 0.0 && sc < __longlong_as_double(0x7ff0000000000000LL)) inv = 1.0 / sc;
+    }
     for (i64 j = blockIdx.y; j < n; j += gridDim.y)
         for (i64 i = (i64)blockIdx.x * 256 + threadIdx.x; i < m; i += (i64)gridDim.x * 256) {
-            const double a2 = (double)scalar_traits<T>::abs2(A[i + j * lda]);
-            if (MODE == 0) acc += a2;
-            else acc = acc > a2 ? acc : a2;
+            if (MODE == 0) {
+                const double ab = abs_entry<T>(A[i + j * lda]) * inv;
+                acc += ab * ab;
+            } else {
+                acc = nanmax(acc, abs_entry<T>(A[i + j * lda]));
+            }
         }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double other = __shfl_xor_sync(0xffffffffu, acc, o);
         if (MODE == 0) acc += other;
-        else acc = acc > other ? acc : other;
+        else acc = nanmax(acc, other);
     }
     __shared__ double ws[8];
     if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
@@ -208,20 +227,39 @@ __global__ void __launch_bounds__(256) reduce_kernel(i64 m, i64 n, const T* __re
         double r = ws[0];
         for (int w = 1; w < 8; ++w) {
             if (MODE == 0) r += ws[w];
-            else r = r > ws[w] ? r : ws[w];
+            else r = nanmax(r, ws[w]);
         }
         if (MODE == 0) atomicAdd(out, r);
-        else atomic_max_nonneg(out, sqrt(r));
+        else atomic_max_nonneg(out, r);
     }
 }
 
 template <class T, int MODE>
-void reduce_t(i64 m, i64 n, const void* A, i64 lda, double* out, cudaStream_t s) {
+void reduce_t(i64 m, i64 n, const void* A, i64 lda, const double* scale_dev, double* out, cudaStream_t s) {
     if (m <= 0 || n <= 0) return;
     i64 gx = ceil_div(m, 256);
     if (gx > 64) gx = 64;
     dim3 grid((unsigned)gx, (unsigned)(n < 256 ? n : 256));
-    reduce_kernel<T, MODE><<<grid, 256, 0, s>>>(m, n, (const T*)A, lda, out);
+    reduce_kernel<T, MODE><<<grid, 256, 0, s>>>(m, n, (const T*)A, lda, scale_dev, out);
+    ELB_LAUNCH_CHECK();
+}
+
+// first j with A(j,j) == 0 -> *flag = offset + j + 1 (only the smallest index survives; a flag that is
+// already nonzero from an earlier block of the same solve is kept)
+template <class T>
+__global__ void __launch_bounds__(256) diag_zero_kernel(i64 n, const T* __restrict__ A, i64 lda, i64 offset, int* flag) {
+    __shared__ int first;
+    if (threadIdx.x == 0) first = 0x7fffffff;
+    __syncthreads();
+    for (i64 j = threadIdx.x; j < n; j += 256)
+        if (scalar_traits<T>::is_zero(A[j + j * lda])) atomicMin(&first, (int)j);
+    __syncthreads();
+    if (threadIdx.x == 0 && first != 0x7fffffff) atomicCAS(flag, 0, (int)(offset + first + 1));
+}
+template <class T>
+void diag_zero_t(i64 n, const void* A, i64 lda, i64 offset, int* flag, cudaStream_t s) {
+    if (n <= 0) return;
+    diag_zero_kernel<T><<<1, 256, 0, s>>>(n, (const T*)A, lda, offset, flag);
     ELB_LAUNCH_CHECK();
 }
 
@@ -292,14 +330,24 @@ int elb200_fill_hash(int dtype, int kind, int64_t m, int64_t n, void* A, int64_t
     });
 }
 
+int elb200_diag_zero_check(int dtype, int64_t n, const void* A, int64_t lda, int64_t offset, int* flag_dev,
+                           elb200_stream_t s) {
+    return guarded([&] { DISPATCH_DTYPE(dtype, (diag_zero_t<T>(n, A, lda, offset, flag_dev, (cudaStream_t)s))); });
+}
+
 int elb200_sumsq(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, double* out_dev,
                  elb200_stream_t s) {
-    return guarded([&] { DISPATCH_DTYPE(dtype, (reduce_t<T, 0>(m, n, A, lda, out_dev, (cudaStream_t)s))); });
+    return guarded([&] { DISPATCH_DTYPE(dtype, (reduce_t<T, 0>(m, n, A, lda, nullptr, out_dev, (cudaStream_t)s))); });
+}
+
+int elb200_sumsq_scaled(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, const double* scale_dev,
+                        double* out_dev, elb200_stream_t s) {
+    return guarded([&] { DISPATCH_DTYPE(dtype, (reduce_t<T, 0>(m, n, A, lda, scale_dev, out_dev, (cudaStream_t)s))); });
 }
 
 int elb200_maxabs(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, double* out_dev,
                   elb200_stream_t s) {
-    return guarded([&] { DISPATCH_DTYPE(dtype, (reduce_t<T, 1>(m, n, A, lda, out_dev, (cudaStream_t)s))); });
+    return guarded([&] { DISPATCH_DTYPE(dtype, (reduce_t<T, 1>(m, n, A, lda, nullptr, out_dev, (cudaStream_t)s))); });
 }
 
 }  // extern "C"

@@ -343,6 +343,11 @@ void trsm_device(char side_, char uplo_, char trans_, char diag_, i64 m, i64 n, 
     const i64 na = side == 'L' ? m : n;
     if (lda < (na > 1 ? na : 1) || ldb < (m > 1 ? m : 1))
         throw std::logic_error("trsm: leading dimension too small");
+    // alpha == 0: B := 0 without referencing A (the BLAS definition; 0 * B would keep NaN / Inf)
+    if (st::is_zero(alpha)) {
+        ELB_CUDA(cudaMemset2DAsync(B, sizeof(T) * (size_t)ldb, 0, sizeof(T) * (size_t)m, (size_t)n, s));
+        return;
+    }
     // B := alpha B once, then an alpha-free substitution
     if (!st::is_one(alpha))
         lattice_copy_device<T>(B, B, m, n, 0, 1, ldb, 0, 1, ldb, false, &alpha, false, s);

@@ -64,10 +64,22 @@ int elb200_fill_hash(int dtype, int kind, int64_t m, int64_t n, void* A, int64_t
                      int64_t rowShift, int64_t rowStride, int64_t colShift, int64_t colStride,
                      uint64_t seed, double diag, elb200_stream_t s);
 
+/* The checkIfSingular scan of El::Trsm (src/blas_like/level3/Trsm.cpp:54-60: a host loop over A.Get(j,j)):
+ * if some A(j,j) == 0 and *flag_dev (device int) is still 0, it receives offset + j + 1 for the smallest such j.
+ * The host layer turns a nonzero flag into SingularMatrixException. */
+int elb200_diag_zero_check(int dtype, int64_t n, const void* A, int64_t lda, int64_t offset, int* flag_dev,
+                           elb200_stream_t s);
+
 /* *out_dev (device double) += sum |a_ij|^2 over the local block */
 int elb200_sumsq(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, double* out_dev,
                  elb200_stream_t s);
-/* *out_dev (device double) = max(*out_dev, max |a_ij|); *out_dev must be >= 0 on entry */
+/* *out_dev += sum |a_ij / *scale_dev|^2 (scale_dev: device double, e.g. the result of elb200_maxabs;
+ * NULL, 0 or a non-finite value means 1): second pass of the scaled Frobenius norm
+ * (the reference's UpdateScaledSquare, src/lapack_like/props/Norm/Frobenius.cpp) */
+int elb200_sumsq_scaled(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, const double* scale_dev,
+                        double* out_dev, elb200_stream_t s);
+/* *out_dev (device double) = max(*out_dev, max |a_ij|); *out_dev must be >= 0 on entry.
+ * A NaN entry yields NaN (the reference's MaxNorm propagates NaN too). */
 int elb200_maxabs(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, double* out_dev,
                   elb200_stream_t s);
 

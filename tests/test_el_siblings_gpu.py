@@ -2,22 +2,16 @@
 (elemental_b200/csrc/host/level3.cpp, compositions over Trrk / Gemm / the redistribution engine) -- against the
 reference library (or the numpy restatement that tests/test_oracle_cpu.py pins to it).
 
-NOT YET RUN ON A DEVICE: these entry points were written after the round's GPU budget was spent.  They are skipped
-unless ELB200_RUN_UNVERIFIED=1 so that the suite the driver runs only contains verified parity claims; the first
-GPU trip of the next round runs them (scripts/round2_first_trip.sh) and removes the gate.
+First run on a B200 in round 2 (gpurun_out/r2_siblings.log: 7 passed); the round-1 environment gate is gone.
 
 Tolerance: ||C - C_ref||_F <= 4 k eps ||A||_F ||B||_F as for Gemm; entries outside the triangle bit-identical."""
-import os
-
 import numpy as np
 import pytest
 
 from oracle import elemental_oracle as O
 from oracle import reference_lib as R
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ELB200_RUN_UNVERIFIED") != "1",
-                                 reason="written without GPU access; set ELB200_RUN_UNVERIFIED=1 to run")]
+pytestmark = pytest.mark.gpu
 
 ORI = {"N": 0, "T": 1, "C": 2}
 UL = {"L": 0, "U": 1}
