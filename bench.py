@@ -424,7 +424,7 @@ def main():
             "roofline": {"bound": "tensor", "achieved": kernel_tf, "peak": dmma_peak_tf, "unit": "TFLOP/s",
                          "frac": kernel_tf / dmma_peak_tf if dmma_peak_tf else None, "traffic": traffic,
                          "algorithmic_bytes_per_launch": 8.0 * (lh_ * nb + nb * lw_ + 2.0 * lh_ * lw_),
-                         "kernel": "elb200::gemm_f64_tma_kernel (persistent, TMA-fed DMMA.8x8x4, L2 red epilogue)",
+                         "kernel": "elb200::gemm_f64_ws_kernel (persistent, TMA-fed DMMA.8x8x4, tile-info ring, L2 red epilogue)",
                          "launches": int(kcount.value), "kernel_ms_per_step": kms.value / args.steps,
                          "kernel_share_of_step": kms.value / ms if ms else None,
                          "flops_per_launch": kflops.value / max(kcount.value, 1),

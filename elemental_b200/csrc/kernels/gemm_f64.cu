@@ -25,11 +25,7 @@
 namespace elb200 {
 extern int g_dgemm_config;
 extern int g_dgemm_last_kernel;
-// gemm_f64_tma.cu: persistent warp-specialised TMA kernel; false when the operands are not TMA-eligible
-bool dgemm_tma_device(int mode, bool ta, bool tb, i64 m, i64 n, i64 k, double alpha, const double* A, i64 lda,
-                      const double* B, i64 ldb, double beta, double* C, i64 ldc, i64 gi0, i64 gis, i64 gj0, i64 gjs,
-                      double flops, cudaStream_t s);
-// gemm_f64_ws.cu: third generation (dedicated producer warp); same contract
+// gemm_f64_ws.cu: persistent TMA-fed kernel; false when the operands are not TMA-eligible
 bool dgemm_ws_device(int mode, bool ta, bool tb, i64 m, i64 n, i64 k, double alpha, const double* A, i64 lda,
                      const double* B, i64 ldb, double beta, double* C, i64 ldc, i64 gi0, i64 gis, i64 gj0, i64 gjs,
                      double flops, cudaStream_t s);
@@ -387,18 +383,11 @@ void dgemm_device(int mode, char transA, char transB, i64 m, i64 n, i64 k, doubl
         }
         a.flops = 2.0 * inside * double(a.k);
     }
-    // default: the persistent TMA kernel (gemm_f64_tma.cu); the cp.async kernel below serves
+    // default: the persistent TMA kernel (gemm_f64_ws.cu); the cp.async kernel below serves
     // operands TMA cannot address (odd leading dimension / 8-byte-aligned base) and cfg 1 / 2
     if (g_dgemm_config == 0 || g_dgemm_config == 3) {
         if (dgemm_ws_device(mode, ta, tb, m, n, a.k, alpha, A, lda, B, ldb, beta, C, ldc, gi0, gis, gj0, gjs,
                             a.flops, s)) {
-            g_dgemm_last_kernel = 2;
-            return;
-        }
-    }
-    if (g_dgemm_config == 4) {  // second-generation TMA kernel (kept for A/B measurements)
-        if (dgemm_tma_device(mode, ta, tb, m, n, a.k, alpha, A, lda, B, ldb, beta, C, ldc, gi0, gis, gj0, gjs,
-                             a.flops, s)) {
             g_dgemm_last_kernel = 2;
             return;
         }

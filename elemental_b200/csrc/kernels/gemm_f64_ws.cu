@@ -1,9 +1,10 @@
 // FP64 GEMM / TRRK, third generation: persistent TMA-fed DMMA kernel with a non-blocking producer and a tile-info ring.
 //
-// Same contract as gemm_f64_tma.cu (replaces blas::Gemm<double> -> dgemm_, reference
+// Same contract as gemm_f64.cu (replaces blas::Gemm<double> -> dgemm_, reference
 // src/core/imports/blas/Gemm.hpp:431, and with MODE != 0 the LocalTrrk recursion of
 // src/blas_like/level3/Trrk/Local.hpp:782-830), built from what the per-warp phase clocks and the ncu
-// source page of the second generation showed on the rank-Blocksize() update (profiles/r02_dgemm_phase_clocks.txt):
+// source page of the second generation (round 1's gemm_f64_tma.cu) showed on the rank-Blocksize() update
+// (profiles/r02_dgemm_phase_clocks_gen2.txt, r02_dmma_loop_variants.txt):
 //   * the warp that issued the TMA loads spent 20 % of its time doing so (9 UTMALDG per k-stage, each behind
 //     an ELECT / R2UR sequence) and, being a consumer too, was the slowest warp of its group: every other
 //     warp then waited 8-18 % of its time for stages that were issued late;
@@ -29,7 +30,7 @@
 //     classified on the host.
 // Shared-memory layouts, the conflict-free fragment reads with their row permutations and the L2 reduction
 // epilogue (red.global.add.f64: C += alpha acc performed by the L2 atomic unit, one writer per entry, hence
-// deterministic) are those of gemm_f64_tma.cu:
+// deterministic) are those of the second generation:
 //   K-major operand (A 'T' / B 'N'): one box [rows][16 k], row pitch 128 B, 16-byte chunk index XORed with
 //     (row & 7); an m8n8k4 fragment takes its 8 rows in the order {0,2,4,6,1,3,5,7}.
 //   MN-major operand (A 'N' / B 'T'): boxes [16 k][16 rows], pitch 128 B, chunk XORed with (k & 7); a fragment
@@ -154,7 +155,9 @@ __device__ __forceinline__ double flip_sign(double x, unsigned flip) {
     return __hiloint2double(__double2hiint(x) ^ (int)flip, __double2loint(x));
 }
 
-// ---- row permutations (see gemm_f64_tma.cu) ----
+// ---- row permutations ----
+// K-major operand: fragment f (8 rows) of a warp takes rows base + 8 f + PK[x], x = MMA row index
+// MN-major operand: fragment f takes rows base + 16 (f >> 1) + 4 (f & 1) + QM[x]
 __device__ __forceinline__ int permK(int x) { return ((x & 3) << 1) | (x >> 2); }
 __device__ __forceinline__ int permM(int x) { return ((x & 2) << 2) | (x & 1) | ((x & 4) >> 1); }  // {0,1,8,9,2,3,10,11}
 template <bool KMAJOR>
@@ -696,4 +699,12 @@ bool dgemm_ws_device(int mode, bool ta, bool tb, i64 m, i64 n, i64 k, double alp
 
 }  // namespace elb200
 
-extern "C" int elb200_dgemm_ws_last_maps(void) { return elb200::g_last_3d; }
+extern "C" {
+// bit 0: A of the last launch used the single-box 3-D tensor map, bit 1: B did
+int elb200_dgemm_ws_last_maps(void) { return elb200::g_last_3d; }
+// bit 4: never use the L2 reduction epilogue; bit 10: phase-clock diagnostic build (NN only); bits 20..25: rasterisation
+// band width; bits 26..29: 1 = no group stagger, v > 1 = stagger of (v - 1) microseconds
+void elb200_dgemm_set_debug_flags(int f) { elb200::g_dgemm_ws_flags = f; }
+// device buffer of (grid * 16 warps * 8) u64 for the phase-clock diagnostic
+void elb200_dgemm_set_profile_buffer(void* p) { elb200::g_dgemm_ws_prof = (unsigned long long*)p; }
+}

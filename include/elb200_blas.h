@@ -65,6 +65,14 @@ int elb200_gemm_profile_read(double* total_ms, long long* launches, double* flop
 void elb200_dgemm_set_config(int cfg);
 /* which kernel the last elb200_dgemm / dtrrk / dsyrk call launched: 1 cp.async, 2 TMA */
 int elb200_dgemm_last_kernel(void);
+/* Debugging aids of the persistent TMA kernel (gemm_f64_ws.cu).  Flags: bit 4 = never use the L2 reduction epilogue
+ * (tests compare it with the load-add-store form bit for bit), bit 10 = phase-clock diagnostic build (NN only),
+ * bits 20..25 = rasterisation band width, bits 26..29 = 1: no group stagger, v > 1: stagger of v - 1 microseconds.
+ * The profile buffer is a device array of (grid x 16 warps x 8) unsigned 64-bit counters for the phase clocks.
+ * elb200_dgemm_ws_last_maps: bit 0 / 1 = A / B of the last launch used the single-box 3-D tensor map. */
+void elb200_dgemm_set_debug_flags(int flags);
+void elb200_dgemm_set_profile_buffer(void* device_u64);
+int elb200_dgemm_ws_last_maps(void);
 
 /* ---- GEMM: C := alpha op(A) op(B) + beta C ---------------------------- */
 /* trans in {'N','T','C'}; for real types 'C' == 'T' (blas/Gemm.hpp:386-387) */

@@ -102,25 +102,3 @@ def test_trmm(El, dt):
                     El.Trmm(LR[side], UL[uplo], ORI[orient], DG[diag], alpha, dA, dB)
                     El.PopBlocksizeStack()
                     assert np.linalg.norm(dB.ToGlobal() - ref) <= _tol(ka, dt, A, B0), (dt, side, uplo, orient, diag)
-
-
-def test_dgemm_prefetch_experiment_kernel_is_bit_identical():
-    """gemm_f64_tma.cu MODE 5 (elb200_dgemm_set_debug_flags(512): fragment loads one k-step ahead, NN only) issues the
-    same DMMAs in the same order as the default kernel, so C must be bit-identical -- also written without GPU access."""
-    import ctypes as C
-    import gpuutil as G
-    from elemental_b200._lib import lib
-    L = lib()
-    rng = np.random.default_rng(3)
-    try:
-        for (m, n, k) in [(128, 64, 16), (256, 192, 128), (300, 200, 70), (1024, 512, 256)]:
-            A, B, C0 = G.rand(rng, m, k, np.float64), G.rand(rng, k, n, np.float64), G.rand(rng, m, n, np.float64)
-            outs = []
-            for flags in (0, 512):
-                L.elb200_dgemm_set_debug_flags(flags)
-                dA, dB, dC = G.DevMat(A, m + (m % 2)), G.DevMat(B, k + (k % 2)), G.DevMat(C0, m + 2)
-                G.gemm("N", "N", -1.0, dA, dB, 1.0, dC, k)
-                outs.append(dC.get())
-            assert np.array_equal(outs[0], outs[1]), (m, n, k)
-    finally:
-        L.elb200_dgemm_set_debug_flags(0)
