@@ -55,7 +55,9 @@ def parse():
     ap.add_argument("--no-orient", action="store_true", help="skip the NT / TN orientations of configs[1]")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-n", type=int, default=12288, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-k", type=int, default=1024,
+                    help="summation indices of the bounded CPU sample (the reference runs C += A(:, :cpu_k) B(:cpu_k, :) at the full m = n)")
+    ap.add_argument("--e2e-serial", action="store_true", help="also time the unpipelined host path (3 copies in, Gemm, 1 copy out)")
     return ap.parse_args()
 
 
@@ -101,44 +103,50 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # the reference's own CPU path (oracle/_ref), used for cpu_baseline and --impl reference
 # ---------------------------------------------------------------------------
-def cpu_reference_gemm(n, nb, steps, warmup):
+def cpu_reference_gemm(n, nb, steps, warmup, ksample):
+    """The reference's own El::Gemm (SUMMA_C, nb) on the box's host cores, on a bounded sample of the SAME workload:
+    the m = n = `n` update C += A(:, 0:ksample) B(0:ksample, :) -- the first ksample / nb of the n / nb rank-nb panel
+    steps of the full product, same C, same panel shape, alpha = beta = 1 as on the GPU arm."""
     from oracle import elemental_oracle as O
     from oracle import reference_lib as R
     cores = os.cpu_count() or 1
     if R.available():
         R.set_threads(cores)
         kind, info = "reference", R.info()
-        run = lambda A, B, Cm: R.gemm("N", "N", 3.0, A, B, 4.0, Cm, nb=nb, alg=3)
+        run = lambda A, B, Cm: R.gemm("N", "N", 1.0, A, B, 1.0, Cm, nb=nb, alg=3)
         threads = R.info()["threads"]
         blas = f"OpenBLAS core {info['corename']}"
     else:
         kind, threads, blas = "port", 1, "numpy"
-        run = lambda A, B, Cm: O.gemm("N", "N", 3.0, A, B, 4.0, Cm, nb=nb, alg=3)
+        run = lambda A, B, Cm: O.gemm("N", "N", 1.0, A, B, 1.0, Cm, nb=nb, alg=3)
     rng = np.random.default_rng(0)
-    A = np.asfortranarray(rng.uniform(-1, 1, (n, n)))
-    B = np.asfortranarray(rng.uniform(-1, 1, (n, n)))
-    Cm = np.asfortranarray(rng.uniform(-1, 1, (n, n)))
+    A = np.asfortranarray(rng.uniform(-1, 1, (n, ksample)))
+    B = np.asfortranarray(rng.uniform(-1, 1, (ksample, n)))
+    Cm = np.empty((n, n), order="F")
+    Cm[:] = 0.5
     for _ in range(warmup):
         run(A, B, Cm)
     t0 = time.perf_counter()
     for _ in range(steps):
         run(A, B, Cm)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return {"value": 2.0 * n ** 3 / dt / 1e9, "unit": "GFLOP/s", "cores": int(threads), "kind": kind,
-            "sample": f"El::Gemm NN double m=n=k={n} nb={nb} GEMM_SUMMA_C on a 1x1 Grid, {blas}, "
-                      f"{steps} call(s), {dt:.2f} s each"}, dt
+    return {"value": 2.0 * n * n * ksample / dt / 1e9, "unit": "GFLOP/s", "cores": int(threads), "kind": kind,
+            "sample": f"El::Gemm NN double GEMM_SUMMA_C nb={nb} on a 1x1 Grid, m=n={n} with the first {ksample} of the "
+                      f"{n} summation indices ({ksample // nb} of {n // nb} rank-{nb} panel steps of the same update), "
+                      f"alpha=beta=1, {blas}, {warmup} warm-up + {steps} timed call(s), {dt:.2f} s each"}, dt
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, dt = cpu_reference_gemm(args.cpu_n, args.nb, max(args.steps, 1), min(args.warmup, 1))
+    steps, warmup = max(args.steps, 1), max(0, min(args.warmup, 3))
+    base, dt = cpu_reference_gemm(args.n, args.nb, steps, warmup, args.cpu_k)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "GFLOP/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"El::Gemm NN double m=n=k={args.n} GEMM_SUMMA_C nb={args.nb}",
-                       "reference_sample": base["sample"], "grid": "1x1 (CPU)"},
+            "config": {"workload": f"El::Gemm NN double m=n=k={args.n} GEMM_SUMMA_C nb={args.nb} on DistMatrix<double,MC,MR>",
+                       "reference_sample": base["sample"], "grid": "1x1 (CPU)", "alpha": 1.0, "beta": 1.0},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -233,14 +241,49 @@ def main():
     # launch shape (profiles/r01_dgemm_update_traffic.json, written by scripts/ncu_traffic.py)
     traffic = None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_dgemm_update_traffic.json")))
-        if prof.get("m") == (n + r - 1) // r and prof.get("n") == (n + c - 1) // c and prof.get("k") == nb:
-            traffic = prof["dram_bytes_per_launch"]
+        for fn_ in ("r02_dgemm_update_traffic.json", "r01_dgemm_update_traffic.json"):
+            path_ = os.path.join(ROOT, "profiles", fn_)
+            if not os.path.exists(path_):
+                continue
+            for prof in (lambda j: j if isinstance(j, list) else [j])(json.load(open(path_))):
+                if prof.get("m") == (n + r - 1) // r and prof.get("n") == (n + c - 1) // c and prof.get("k") == nb:
+                    traffic = prof["dram_bytes_per_launch"]
+                    break
+            if traffic is not None:
+                break
     except Exception:
         pass
     flops_step = 2.0 * n ** 3
     value = flops_step * args.steps / (ms * 1e-3) / 1e9
     kernel_tf = kflops.value / (kms.value * 1e-3) / 1e12 if kms.value > 0 else 0.0
+
+    # ---- parity of the timed product, at every N, outside the timed region: the reference's own check
+    #      (tests/blas_like/Gemm.cpp:13-42) ||(alpha op(A) op(B) + beta C0) X - C X||_F / ||C X||_F with 16 hash-filled
+    #      right-hand sides.  C holds C0 + T op(A) op(B) after T calls with alpha = beta = 1. ----
+    def gemm_parity(oa, ob, A, B, Cfinal, T, seedC=3):
+        nr = 16
+        X = El.DistMatrix(np.float64, El.MC, El.MR, grid, n, nr).HashFill(0, 9)
+        Z = El.DistMatrix(np.float64, El.MC, El.MR, grid, n, nr)
+        Y = El.DistMatrix(np.float64, El.MC, El.MR, grid, n, nr)
+        El.Gemm(ob, El.NORMAL, 1.0, B, X, 0.0, Z)            # Z = op(B) X
+        El.Gemm(El.NORMAL, El.NORMAL, 1.0, Cfinal, X, 0.0, Y)  # Y = C X
+        den = El.FrobeniusNorm(Y)
+        El.Gemm(oa, El.NORMAL, -float(T), A, Z, 1.0, Y)        # Y -= T op(A) Z
+        C0 = El.DistMatrix(np.float64, El.MC, El.MR, grid, n, n).HashFill(0, seedC)
+        El.Gemm(El.NORMAL, El.NORMAL, -1.0, C0, X, 1.0, Y)     # Y -= C0 X
+        res = El.FrobeniusNorm(Y) / den if den > 0 else float("nan")
+        del C0, X, Z, Y
+        torch.cuda.empty_cache()
+        return float(res)
+
+    parity = {"def": "||(alpha op(A) op(B) + beta C0) X - C X||_F / ||C X||_F, 16 hash-filled right-hand sides "
+                     "(the reference's check, tests/blas_like/Gemm.cpp:13-42), C after all warm-up + timed calls",
+              "tolerance": 100 * n * 2.0 ** -52}
+    try:
+        parity["NN"] = gemm_parity(El.NORMAL, El.NORMAL, A, B, Cm, args.warmup + args.steps)
+        parity["ok"] = bool(parity["NN"] <= parity["tolerance"])
+    except Exception as ex:
+        parity["error"] = repr(ex)[:200]
 
     # ---- DPOTRF (BASELINE.json configs[2]) ----
     potrf = None
@@ -282,7 +325,8 @@ def main():
         torch.cuda.empty_cache()
         El.SetBlocksize(nb)
 
-    # ---- end-to-end: HOST buffers in, HOST result out, through the public API ----
+    # ---- end-to-end: HOST buffers in, HOST result out, through the public API (El.GemmHost = ElGemmDistHost_d):
+    #      the [MC,MR] local matrices live in pinned host memory, as a reference DistMatrix's buffers do ----
     e2e = None
     if not args.no_e2e:
         A = El.DistMatrix(np.float64, El.MC, El.MR, grid, n, n).HashFill(0, 1)
@@ -290,16 +334,27 @@ def main():
         Cm = El.DistMatrix(np.float64, El.MC, El.MR, grid, n, n).HashFill(0, 3)
         lh, lw = A.LocalHeight(), A.LocalWidth()
         pinned = [torch.empty((lw, max(lh, 1)), dtype=torch.float64, pin_memory=True) for _ in range(3)]
-        host = [t.numpy().T for t in pinned]          # Fortran-ordered views of the pinned buffers
         for M, t in zip((A, B, Cm), pinned):
-            _check_copy = L.ElDistMatrixLocalToHost_d(M._h, C.c_void_p(t.data_ptr()), max(lh, 1))
-        out_pinned = torch.empty((lw, max(lh, 1)), dtype=torch.float64, pin_memory=True)
+            L.ElDistMatrixLocalToHost_d(M._h, C.c_void_p(t.data_ptr()), max(lh, 1))
+        serial = None
+        if args.e2e_serial:
+            out_pinned = torch.empty((lw, max(lh, 1)), dtype=torch.float64, pin_memory=True)
+
+            def serial_step():
+                for M, t in zip((A, B, Cm), pinned):
+                    L.ElDistMatrixLocalFromHost_d(M._h, C.c_void_p(t.data_ptr()), max(lh, 1))
+                El.Gemm(El.NORMAL, El.NORMAL, 1.0, A, B, 1.0, Cm, El.GEMM_SUMMA_C)
+                L.ElDistMatrixLocalToHost_d(Cm._h, C.c_void_p(out_pinned.data_ptr()), max(lh, 1))
+            timed(serial_step, 1)
+            sms = timed(serial_step, 1)
+            serial = {"value": flops_step / (sms * 1e-3) / 1e9, "ms_per_step": sms,
+                      "what": "3 x LocalFromHost, El::Gemm, LocalToHost back to back (round 1's e2e)"}
+            del out_pinned
+        del A, B, Cm
+        torch.cuda.empty_cache()
 
         def e2e_step():
-            for M, t in zip((A, B, Cm), pinned):
-                L.ElDistMatrixLocalFromHost_d(M._h, C.c_void_p(t.data_ptr()), max(lh, 1))
-            El.Gemm(El.NORMAL, El.NORMAL, 1.0, A, B, 1.0, Cm, El.GEMM_SUMMA_C)
-            L.ElDistMatrixLocalToHost_d(Cm._h, C.c_void_p(out_pinned.data_ptr()), max(lh, 1))
+            El.GemmHost(El.NORMAL, El.NORMAL, 1.0, grid, n, n, n, pinned[0], pinned[1], 1.0, pinned[2], El.GEMM_SUMMA_C)
 
         e2e_steps = max(1, min(args.steps, 2))
         timed(e2e_step, 1)
@@ -307,12 +362,27 @@ def main():
         bytes_local = lh * lw * 8
         e2e = {"value": flops_step * e2e_steps / (ems * 1e-3) / 1e9, "unit": "GFLOP/s",
                "h2d_bytes_per_step": int(3 * bytes_local * N), "d2h_bytes_per_step": int(bytes_local * N),
-               "ms_per_step": ems / e2e_steps, "steps": e2e_steps}
-        del A, B, Cm, pinned, out_pinned
+               "ms_per_step": ems / e2e_steps, "steps": e2e_steps,
+               "api": "El.GemmHost -> ElGemmDistHost_d: pinned host [MC,MR] local matrices in, C back in host memory on "
+                      "return; C streamed through HBM in column bands, copies overlapped with the SUMMA updates"}
+        if serial:
+            e2e["unpipelined"] = serial
+        # the streamed result is checked too: the host C after T calls against the device product of the same inputs
+        try:
+            A = El.DistMatrix(np.float64, El.MC, El.MR, grid, n, n).HashFill(0, 1)
+            B = El.DistMatrix(np.float64, El.MC, El.MR, grid, n, n).HashFill(0, 2)
+            Ch = El.DistMatrix(np.float64, El.MC, El.MR, grid, n, n)
+            L.ElDistMatrixLocalFromHost_d(Ch._h, C.c_void_p(pinned[2].data_ptr()), max(lh, 1))
+            e2e["parity_NN"] = gemm_parity(El.NORMAL, El.NORMAL, A, B, Ch, 1 + e2e_steps)
+            del A, B, Ch
+        except Exception as ex:
+            e2e["parity_error"] = repr(ex)[:200]
+        del pinned
+        torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and N == 1 and not args.no_cpu:
-        cpu, _ = cpu_reference_gemm(args.cpu_n, nb, 1, 1)
+        cpu, _ = cpu_reference_gemm(n, nb, 1, 1, min(args.cpu_k, n))
 
     def _guard(fn, name):
         try:
@@ -399,9 +469,14 @@ def main():
         El.SetBlocksize(nb)
         for name, oa, ob in (("NT", El.NORMAL, El.TRANSPOSE), ("TN", El.TRANSPOSE, El.NORMAL)):
             fn = lambda: El.Gemm(oa, ob, 1.0, A, B, 1.0, Cm, El.GEMM_SUMMA_C)
+            Cm.HashFill(0, 3)
             timed(fn, 1)
             oms = timed(fn, 1)
             out[name] = {"ms": oms, "value": flops_step / (oms * 1e-3) / 1e9, "unit": "GFLOP/s"}
+            try:
+                out[name]["parity"] = gemm_parity(oa, ob, A, B, Cm, 2)
+            except Exception as ex:
+                out[name]["parity_error"] = repr(ex)[:200]
         del A, B, Cm
         torch.cuda.empty_cache()
         return out
@@ -434,6 +509,7 @@ def main():
                                         "MEASURED_PEAKS.json has no FP64 figure",
                          "cublas_dgemm_8192_tflops": cublas_tf, "nominal_fp64_tensor_tflops": 40.0},
             "gpu_launches": launches,
+            "parity": parity,
             "redist": stats,
             "clocks": clocks,
         }

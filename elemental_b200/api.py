@@ -379,6 +379,30 @@ def Gemm(orientA, orientB, alpha, A: DistMatrix, B: DistMatrix, beta, Cm: DistMa
            "ElGemmXDist")
 
 
+_SUF = {"float32": "s", "float64": "d", "complex64": "c", "complex128": "z"}
+
+
+def GemmHost(orientA, orientB, alpha, grid: Grid, m, n, k, A, B, beta, Cm, alg=GEMM_DEFAULT):
+    """El::Gemm for HOST-resident [MC,MR] local matrices: A, B, Cm are this process's column-major local matrices
+    (numpy arrays in Fortran order, or torch CPU tensors holding the transpose; pinned memory for the copy overlap),
+    m, n, k the global sizes of op(A) op(B).  Streams C through HBM in column bands with the host copies
+    overlapped (ElGemmDistHost_*, csrc/host/stream_gemm.cpp); Cm is complete on return."""
+    _sync_stream()
+
+    def ptr_ld(x):
+        if isinstance(x, np.ndarray):
+            if not x.flags.f_contiguous and x.ndim == 2 and min(x.shape) > 1:
+                raise ValueError("GemmHost needs column-major (Fortran-ordered) local matrices")
+            return x.ctypes.data_as(C.c_void_p), max(int(x.strides[1] // x.itemsize) if x.ndim == 2 and x.shape[1] > 1 else x.shape[0], 1), x.dtype
+        # torch tensor of shape (local width, ld): row j is local column j
+        return C.c_void_p(x.data_ptr()), max(int(x.stride(0)), 1), np.dtype(str(x.dtype).replace("torch.", ""))
+
+    (pa, lda, dt), (pb, ldb, _), (pc, ldc, _) = ptr_ld(A), ptr_ld(B), ptr_ld(Cm)
+    fn = getattr(lib(), "ElGemmDistHost_" + _SUF[np.dtype(dt).name])
+    _check(fn(orientA, orientB, _scalar(dt, alpha), grid._h, int(m), int(n), int(k), pa, lda, pb, ldb,
+              _scalar(dt, beta), pc, ldc, alg), "ElGemmDistHost")
+
+
 def Syrk(uplo, orient, alpha, A: DistMatrix, beta, Cm: DistMatrix):
     _sync_stream()
     dt = _same(A, Cm).dtype

@@ -185,6 +185,19 @@ ElError ElRedistStats(uint64_t out[8], bool reset) {
                  static_cast<GemmAlgorithm>(alg));                                                                 \
         });                                                                                                        \
     }                                                                                                              \
+    ElError ElGemmDistHost_##SUF(ElOrientation oA, ElOrientation oB, SCALAR alpha, ElConstGrid grid, ElInt m, ElInt n, \
+                                 ElInt k, const SCALAR* A, ElInt lda, const SCALAR* B, ElInt ldb, SCALAR beta,     \
+                                 SCALAR* C, ElInt ldc, ElGemmAlgorithm alg) {                                      \
+        return Try([&] {                                                                                           \
+            HostLocalMatrix<T> hA{O(oA) == NORMAL ? m : k, O(oA) == NORMAL ? k : m,                                \
+                                  const_cast<T*>(reinterpret_cast<const T*>(A)), lda};                             \
+            HostLocalMatrix<T> hB{O(oB) == NORMAL ? k : n, O(oB) == NORMAL ? n : k,                                \
+                                  const_cast<T*>(reinterpret_cast<const T*>(B)), ldb};                             \
+            HostLocalMatrix<T> hC{m, n, reinterpret_cast<T*>(C), ldc};                                             \
+            GemmHost(O(oA), O(oB), Sc<T, SCALAR>(alpha), *G(grid), hA, hB, Sc<T, SCALAR>(beta), hC,               \
+                     static_cast<GemmAlgorithm>(alg));                                                             \
+        });                                                                                                        \
+    }                                                                                                              \
     ElError ElSyrkDist_##SUF(ElUpperOrLower uplo, ElOrientation o, SCALAR alpha, ElConstDistMatrix_##SUF A,        \
                              SCALAR beta, ElDistMatrix_##SUF C) {                                                  \
         return Try([&] { Syrk(UL(uplo), O(o), Sc<T, SCALAR>(alpha), *CM_##SUF(A), Sc<T, SCALAR>(beta), *M_##SUF(C), false); }); \

@@ -56,6 +56,25 @@ struct Event {
     void Record(cudaStream_t s) { ELB_CUDA(cudaEventRecord(e, s)); }
     void Wait(cudaStream_t s) { ELB_CUDA(cudaStreamWaitEvent(s, e, 0)); }
 };
+// A device int, zeroed on construction on the current stream; Read() synchronises that stream.  The
+// kernels that can fail numerically (potrf pivots, the zero-diagonal scan of Trsm) write it only when it
+// still holds 0, so one flag serves a whole blocked sweep and the host raises the exception once.
+struct DeviceFlag {
+    int* dev_ = nullptr;
+    DeviceFlag() {
+        dev_ = (int*)elb200::scratch_alloc(sizeof(int), stream());
+        ELB_CUDA(cudaMemsetAsync(dev_, 0, sizeof(int), stream()));
+    }
+    ~DeviceFlag() { if (dev_) cudaFreeAsync(dev_, stream()); }
+    DeviceFlag(const DeviceFlag&) = delete;
+    DeviceFlag& operator=(const DeviceFlag&) = delete;
+    int Read() {
+        int h = 0;
+        ELB_CUDA(cudaMemcpyAsync(&h, dev_, sizeof(int), cudaMemcpyDeviceToHost, stream()));
+        ELB_CUDA(cudaStreamSynchronize(stream()));
+        return h;
+    }
+};
 // ELB200_TRACE=1: the factorisation drivers synchronise around each phase and print the summed
 // device time per phase at the end (a diagnostic; it serialises the look-ahead)
 struct PhaseTimer {

@@ -33,20 +33,7 @@ AbstractDistMatrix<T> View(AbstractDistMatrix<T>& A, Int i, Int j, Int h, Int w)
     return V;
 }
 
-struct InfoFlag {
-    int* dev_ = nullptr;
-    InfoFlag() {
-        dev_ = (int*)elb200::scratch_alloc(sizeof(int), dev::stream());
-        ELB_CUDA(cudaMemsetAsync(dev_, 0, sizeof(int), dev::stream()));
-    }
-    ~InfoFlag() { if (dev_) cudaFreeAsync(dev_, dev::stream()); }
-    int Read() {
-        int h = 0;
-        ELB_CUDA(cudaMemcpyAsync(&h, dev_, sizeof(int), cudaMemcpyDeviceToHost, dev::stream()));
-        ELB_CUDA(cudaStreamSynchronize(dev::stream()));
-        return h;
-    }
-};
+typedef dev::DeviceFlag InfoFlag;
 
 template <typename F>
 void LocalPotrf(UpperOrLower uplo, Matrix<F>& A, int* info, Int colOffset) {

@@ -497,16 +497,36 @@ void Trmm(LeftOrRight side, UpperOrLower uplo, Orientation o, UnitOrNonUnit diag
 // ---------------------------------------------------------------------------
 // Trsm
 // ---------------------------------------------------------------------------
+namespace {
+// the zero-diagonal scan of Trsm.cpp:54-60 on the device: flag <- offset + j + 1 for the first A(j,j) == 0
 template <typename F>
-void Trsm(LeftOrRight side, UpperOrLower uplo, Orientation o, UnitOrNonUnit diag, F alpha, const Matrix<F>& A,
-          Matrix<F>& B, bool checkIfSingular) {
+void ScanDiagonal(const Matrix<F>& A, int* flagDev, Int offset) {
+    dev::c_check(elb200_diag_zero_check(dev::Code<F>(), A.Height(), A.LockedBuffer(), A.LDim(), offset, flagDev,
+                                        (elb200_stream_t)dev::stream()),
+                 "elb200_diag_zero_check");
+}
+template <typename F>
+void LocalTrsmRaw(LeftOrRight side, UpperOrLower uplo, Orientation o, UnitOrNonUnit diag, F alpha, const Matrix<F>& A,
+                  Matrix<F>& B) {
     const Int na = (side == LEFT) ? B.Height() : B.Width();
     if (A.Height() != A.Width()) LogicError("Triangular matrix must be square");
     if (A.Height() != na) LogicError("Nonconformal Trsm");
-    (void)checkIfSingular;  // a zero diagonal yields inf/nan exactly as ?trsm does
     elb200::trsm_device<dev::D<F>>(LeftOrRightToChar(side), UpperOrLowerToChar(uplo), OrientationToChar(o),
                                    UnitOrNonUnitToChar(diag), B.Height(), B.Width(), dev::val<F>(alpha),
                                    dev::ptr(A.LockedBuffer()), A.LDim(), dev::ptr(B.Buffer()), B.LDim(), dev::stream());
+}
+}  // namespace
+
+template <typename F>
+void Trsm(LeftOrRight side, UpperOrLower uplo, Orientation o, UnitOrNonUnit diag, F alpha, const Matrix<F>& A,
+          Matrix<F>& B, bool checkIfSingular) {
+    if (checkIfSingular && diag != UNIT) {
+        // Trsm.cpp:54-60 throws before the solve
+        dev::DeviceFlag flag;
+        ScanDiagonal(A, flag.dev_, 0);
+        if (flag.Read() != 0) throw SingularMatrixException();
+    }
+    LocalTrsmRaw(side, uplo, o, diag, alpha, A, B);
 }
 template <typename F>
 void LocalTrsm(LeftOrRight side, UpperOrLower uplo, Orientation o, UnitOrNonUnit diag, F alpha,

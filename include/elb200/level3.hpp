@@ -28,6 +28,24 @@ void LocalGemm(Orientation orientA, Orientation orientB, T alpha, const Abstract
 // which SUMMA variant GEMM_DEFAULT resolves to (Gemm/NN.hpp:304-313)
 GemmAlgorithm GemmDefaultAlgorithm(Int m, Int n, Int k);
 
+// ---- GemmHost: the same product for operands whose [MC,MR] local matrices are in HOST memory ----
+// (what a caller of the reference holds: DistMatrix buffers are host allocations there).  height / width are the
+// GLOBAL dimensions, buffer / ldim the column-major local matrix of this process (alignments 0, i.e. what
+// DistMatrix<T>(grid) gives).  C is streamed through HBM in column bands, A in chunks of the summation index, host
+// copies overlapped with the SUMMA updates (csrc/host/stream_gemm.cpp); pinned (page-locked) buffers are needed for
+// the overlap, pageable ones still give the right result.  On return C is complete in host memory.
+template <typename T>
+struct HostLocalMatrix {
+    Int height, width;
+    T* buffer;
+    Int ldim;
+};
+struct GemmHostStats { int bands, chunks; Int bandWidth, chunkWidth; };
+template <typename T>
+void GemmHost(Orientation orientA, Orientation orientB, T alpha, const Grid& grid, const HostLocalMatrix<T>& A,
+              const HostLocalMatrix<T>& B, T beta, const HostLocalMatrix<T>& C, GemmAlgorithm alg = GEMM_DEFAULT,
+              GemmHostStats* stats = nullptr);
+
 // ---- Trrk: triangular rank-k update (src/blas_like/level3/Trrk.cpp, Trrk/Local.hpp) ----
 template <typename T>
 void Trrk(UpperOrLower uplo, Orientation orientA, Orientation orientB, T alpha, const Matrix<T>& A,

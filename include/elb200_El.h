@@ -136,6 +136,14 @@ ElError ElRedistStats(uint64_t out[8], bool reset);
     ElError ElGemmXDist_##SUF(ElOrientation orientationOfA, ElOrientation orientationOfB, SCALAR alpha,     \
                               ElConstDistMatrix_##SUF A, ElConstDistMatrix_##SUF B, SCALAR beta,            \
                               ElDistMatrix_##SUF C, ElGemmAlgorithm alg);                                   \
+    /* El::Gemm on HOST-resident [MC,MR] local matrices (the buffers a reference DistMatrix owns): m, n, k */ \
+    /* are the global sizes of op(A) op(B), A / B / C the column-major local matrices of this process      */ \
+    /* (alignments 0) with leading dimensions lda / ldb / ldc.  Streamed through HBM with the host copies  */ \
+    /* overlapped (csrc/host/stream_gemm.cpp); C is complete in host memory on return.                     */ \
+    ElError ElGemmDistHost_##SUF(ElOrientation orientationOfA, ElOrientation orientationOfB, SCALAR alpha,  \
+                                 ElConstGrid grid, ElInt m, ElInt n, ElInt k, const SCALAR* A, ElInt lda,   \
+                                 const SCALAR* B, ElInt ldb, SCALAR beta, SCALAR* C, ElInt ldc,             \
+                                 ElGemmAlgorithm alg);                                                      \
     ElError ElSyrkDist_##SUF(ElUpperOrLower uplo, ElOrientation orientation, SCALAR alpha,                  \
                              ElConstDistMatrix_##SUF A, SCALAR beta, ElDistMatrix_##SUF C);                 \
     ElError ElHerkDist_##SUF(ElUpperOrLower uplo, ElOrientation orientation, REAL alpha,                    \

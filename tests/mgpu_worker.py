@@ -75,6 +75,21 @@ def main():
                     res = O.gemm_residual(dC.ToGlobal(), ref, k, A, B)
                     if not res <= 1.0:
                         fails.append(f"gemm {dt.__name__} {oa}{ob} alg={alg} res={res}")
+    # 2b. GemmHost: host-resident local matrices streamed in column bands, against the device Gemm (bit-identical
+    #     for alpha = -1, SUMMA_C: the same rank-nb updates in the same order)
+    for (oa, ob) in (("N", "N"), ("N", "T"), ("C", "N")):
+        m, n, k, nb = 260, 520, 400, 32
+        A = O.fill(0, *((m, k) if oa == "N" else (k, m)), 1)
+        B = O.fill(0, *((k, n) if ob == "N" else (n, k)), 2)
+        C0 = O.fill(0, m, n, 3)
+        El.PushBlocksizeStack(nb)
+        dA, dB, dC = dm(A), dm(B), dm(C0)
+        El.Gemm(ORI[oa], ORI[ob], -1.0, dA, dB, 1.0, dC, El.GEMM_SUMMA_C)
+        hA, hB, hC = dA.LocalToHost(), dB.LocalToHost(), dm(C0).LocalToHost()
+        El.GemmHost(ORI[oa], ORI[ob], -1.0, g, m, n, k, hA, hB, 1.0, hC, El.GEMM_SUMMA_C)
+        El.PopBlocksizeStack()
+        if not np.array_equal(hC, dC.LocalToHost()):
+            fails.append(f"gemmhost {oa}{ob}")
     # 3. Cholesky / HPDSolve / Trsm
     for dt in (np.float64, np.complex128):
         n, nb = 300, 64

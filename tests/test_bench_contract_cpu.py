@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "1", "--cpu-n", "768"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                        "--warmup", "1", "--n", "768", "--cpu-k", "256"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.strip().startswith("{")]
     assert len(lines) == 1
@@ -21,12 +21,13 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
         assert key in d, key
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and d["config"]["alpha"] == 1.0 and d["config"]["beta"] == 1.0
+    assert d["warmup"] == 1 and d["steps"] == 1
 
 
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
-                        "--steps", "1", "--warmup", "1", "--cpu-n", "256"], capture_output=True, text=True,
+                        "--steps", "1", "--warmup", "1", "--n", "256", "--cpu-k", "128"], capture_output=True, text=True,
                        timeout=300, cwd=ROOT, env=env)
     assert p.returncode == 0 and p.stdout.strip() == ""

@@ -52,7 +52,7 @@ def _fake_api(calls):
             calls.append(name)
             return ret
         return f
-    for name in ("SetBlocksize", "Gemm", "Cholesky", "CholeskySolveAfter", "HPDSolve"):
+    for name in ("SetBlocksize", "Gemm", "GemmHost", "Cholesky", "CholeskySolveAfter", "HPDSolve"):
         setattr(m, name, rec(name))
     m.FrobeniusNorm = rec("FrobeniusNorm", 1.0)
     m.RedistStats = rec("RedistStats", {"copies": 0})
@@ -117,7 +117,7 @@ def test_own_arm_control_flow_and_json_line(monkeypatch):
     assert len(lines) == 1
     d = json.loads(lines[0])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-                "vs_baseline", "dtype", "data", "config", "roofline", "gpu_launches", "clocks", "e2e", "dpotrf",
+                "vs_baseline", "dtype", "data", "config", "roofline", "gpu_launches", "clocks", "e2e", "dpotrf", "parity",
                 "zhpdsolve", "sgemm_dot", "dgemm_orientations"):
         assert key in d, key
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
@@ -127,6 +127,8 @@ def test_own_arm_control_flow_and_json_line(monkeypatch):
     assert set(d["dgemm_orientations"]) == {"NT", "TN"}
     assert {"3xtf32_tcgen05", "exact_ffma"} <= set(d["sgemm_dot"])
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert "GemmHost" in calls and "NN" in d["parity"] and "parity_NN" in d["e2e"]
+    assert all("parity" in v for v in d["dgemm_orientations"].values())
     # the headline sections run before the extras
     first_extra = min(i for i, c in enumerate(calls) if c == "HPDSolve")
     assert "Cholesky" in calls[:first_extra]

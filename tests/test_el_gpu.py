@@ -58,6 +58,32 @@ def test_gemm_matches_reference_all_variants(El, dt):
                 assert O.gemm_residual(got, ref, k, A, B) <= 1.0, (dt, oa, ob, alg)
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.complex128, np.float32])
+def test_gemm_host_streamed_matches_device_gemm(El, dt):
+    """El.GemmHost (ElGemmDistHost_*: host-resident local matrices, C streamed through HBM in column bands, A in
+    chunks of the summation index) against El.Gemm on device-resident copies of the same inputs.  alpha = -1:
+    bit-identical (same rank-nb updates in the same order); general alpha: the Gemm tolerance."""
+    m, n, k, nb = 210, 300, 200, 32     # 7 bands of 48 columns, 7 chunks of 32 summation indices
+    g = El.Grid()
+    for oa in "NTC":
+        for ob in "NTC":
+            A = O.fill(0, *((m, k) if oa == "N" else (k, m)), 1, dtype=dt)
+            B = O.fill(0, *((k, n) if ob == "N" else (n, k)), 2, dtype=dt)
+            C0 = O.fill(0, m, n, 3, dtype=dt)
+            for alpha, beta, alg in ((-1.0, 1.0, El.GEMM_SUMMA_C), (3.0, 4.0, El.GEMM_SUMMA_C), (-1.0, 0.5, El.GEMM_DEFAULT)):
+                El.PushBlocksizeStack(nb)
+                dA, dB, dC = _dm(El, A), _dm(El, B), _dm(El, C0)
+                El.Gemm(ORI[oa], ORI[ob], alpha, dA, dB, beta, dC, alg)
+                want = dC.ToGlobal()
+                hA, hB, hC = np.asfortranarray(A), np.asfortranarray(B), np.asfortranarray(C0.copy())
+                El.GemmHost(ORI[oa], ORI[ob], alpha, g, m, n, k, hA, hB, beta, hC, alg)
+                El.PopBlocksizeStack()
+                if alpha == -1.0 and alg == El.GEMM_SUMMA_C:
+                    assert np.array_equal(hC, want), (dt, oa, ob, alpha)
+                else:
+                    assert O.gemm_residual(hC, want, k, A, B) <= 1.0, (dt, oa, ob, alpha, alg)
+
+
 def test_gemm_float_3xtf32_mode_summa_dot(El):
     """BASELINE.json configs[4] in miniature: El::Gemm float, tall-skinny k (auto-selects SUMMA_Dot, NN.hpp:305),
     exact-FFMA mode vs 3xTF32 mode, both against the FP64 product.  Tolerance (north_star):
