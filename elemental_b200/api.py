@@ -460,10 +460,22 @@ def Trmm(side, uplo, orient, diag, alpha, A: DistMatrix, B: DistMatrix):
     _check(B._fn("ElTrmmDist")(side, uplo, orient, diag, _scalar(dt, alpha), A._h, B._h), "ElTrmmDist")
 
 
-def Trsm(side, uplo, orient, diag, alpha, A: DistMatrix, B: DistMatrix):
+TRSM_DEFAULT, TRSM_LARGE, TRSM_MEDIUM, TRSM_SMALL = 0, 1, 2, 3
+
+
+def Trsm(side, uplo, orient, diag, alpha, A: DistMatrix, B: DistMatrix, checkIfSingular=False, alg=TRSM_DEFAULT):
+    """El::Trsm(side, uplo, orientation, diag, alpha, A, B, checkIfSingular, alg) (src/blas_like/level3/Trsm.cpp:67-375);
+    raises SingularMatrixException when checkIfSingular finds a zero diagonal entry."""
     _sync_stream()
     dt = _same(A, B).dtype
-    _check(B._fn("ElTrsmDist")(side, uplo, orient, diag, _scalar(dt, alpha), A._h, B._h), "ElTrsmDist")
+    _check(B._fn("ElTrsmXDist")(side, uplo, orient, diag, _scalar(dt, alpha), A._h, B._h, C.c_bool(checkIfSingular),
+                                int(alg)), "ElTrsmXDist")
+
+
+def Trsv(uplo, orient, diag, A: DistMatrix, x: DistMatrix):
+    """El::Trsv(uplo, orientation, diag, A, x) (src/blas_like/level2/Trsv.cpp:47-68)."""
+    _sync_stream()
+    _check(_same(A, x)._fn("ElTrsvDist")(uplo, orient, diag, A._h, x._h), "ElTrsvDist")
 
 
 def Cholesky(uplo, A: DistMatrix):

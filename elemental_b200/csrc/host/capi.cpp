@@ -220,6 +220,18 @@ ElError ElRedistStats(uint64_t out[8], bool reset) {
                  Sc<T, SCALAR>(alpha), *CM_##SUF(A), *M_##SUF(B));                                                 \
         });                                                                                                        \
     }                                                                                                              \
+    ElError ElTrsmXDist_##SUF(ElLeftOrRight side, ElUpperOrLower uplo, ElOrientation o, ElUnitOrNonUnit diag,      \
+                              SCALAR alpha, ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B, bool checkIfSingular, \
+                              ElTrsmAlgorithm alg) {                                                               \
+        return Try([&] {                                                                                           \
+            Trsm(static_cast<LeftOrRight>(side), UL(uplo), O(o), static_cast<UnitOrNonUnit>(diag),                 \
+                 Sc<T, SCALAR>(alpha), *CM_##SUF(A), *M_##SUF(B), checkIfSingular, static_cast<TrsmAlgorithm>(alg)); \
+        });                                                                                                        \
+    }                                                                                                              \
+    ElError ElTrsvDist_##SUF(ElUpperOrLower uplo, ElOrientation o, ElUnitOrNonUnit diag, ElConstDistMatrix_##SUF A, \
+                             ElDistMatrix_##SUF x) {                                                               \
+        return Try([&] { Trsv(UL(uplo), O(o), static_cast<UnitOrNonUnit>(diag), *CM_##SUF(A), *M_##SUF(x)); });    \
+    }                                                                                                              \
     ElError ElSymmDist_##SUF(ElLeftOrRight side, ElUpperOrLower uplo, SCALAR alpha, ElConstDistMatrix_##SUF A,     \
                              ElConstDistMatrix_##SUF B, SCALAR beta, ElDistMatrix_##SUF C) {                       \
         return Try([&] {                                                                                           \

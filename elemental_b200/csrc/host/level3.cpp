@@ -12,6 +12,7 @@
 //              Trrk.cpp:100-116 + Trrk/*.hpp, Syrk.cpp:70-86 + Syrk/*.hpp, Herk.cpp,
 //              Trsm.cpp:67-375 + Trsm/{LLN,LLT,LUN,LUT,RLN,RLT,RUN,RUT}.hpp
 #include <algorithm>
+#include <memory>
 
 #include "dev.hpp"
 #include "elb200/level3.hpp"
@@ -537,91 +538,283 @@ void LocalTrsm(LeftOrRight side, UpperOrLower uplo, Orientation o, UnitOrNonUnit
     Trsm(side, uplo, o, diag, alpha, A.LockedMatrix(), X.Matrix(), checkIfSingular);
 }
 
+namespace {
+
+// One block step of a distributed triangular solve needs L11 = tri(k:k+nb, k:k+nb) replicated and the panel of the
+// triangle that couples block k to the blocks not yet solved.  Both depend only on the (read-only) triangle, so they
+// are formed one step AHEAD on the panel stream (double-buffered), underneath the previous step's update.
 template <typename F>
-void Trsm(LeftOrRight side, UpperOrLower uplo, Orientation o, UnitOrNonUnit diag, F alpha,
-          const AbstractDistMatrix<F>& APre, AbstractDistMatrix<F>& BPre, bool checkIfSingular, TrsmAlgorithm) {
-    AssertSameGrid(APre, BPre);
-    if (APre.Height() != APre.Width()) LogicError("A must be square");
-    if ((side == LEFT ? BPre.Height() : BPre.Width()) != APre.Height()) LogicError("Nonconformal Trsm");
-    Scale(alpha, BPre);  // Trsm.cpp:94
-    ReadProxy<F> AP(APre);
-    ReadWriteProxy<F> XP(BPre);
-    const auto& L = AP.Get();
-    auto& X = XP.Get();
-    const Grid& g = X.Grid();
-    const Int mTri = L.Height();
-    const Int bsize = Blocksize();
-    const bool effLower = (uplo == LOWER) == (o == NORMAL);
-    const bool forward = (side == LEFT) ? effLower : !effLower;
-    AbstractDistMatrix<F> L11(g, STAR, STAR);
-    const Int nblk = (mTri + bsize - 1) / bsize;
-    for (Int step = 0; step < nblk; ++step) {
-        const Int kb = forward ? step : nblk - 1 - step;
-        const Int k = kb * bsize;
-        const Int nb = std::min(bsize, mTri - k);
-        const Int r0 = forward ? k + nb : 0;            // the not-yet-solved part
-        const Int rl = forward ? mTri - (k + nb) : k;
-        {
-            auto L11v = LockedView(L, k, k, nb, nb);
-            Copy(static_cast<const AbstractDistMatrix<F>&>(L11v), L11);  // L11[*,*] <- L11[MC,MR]
+struct TrsmPanels {
+    const AbstractDistMatrix<F>& L;
+    const Grid& g;
+    bool overlap;
+    cudaStream_t mainS, panelS;
+    AbstractDistMatrix<F> L11[2];
+    AbstractDistMatrix<F> Lp[2];
+    dev::Event ready[2], freed[2], fork;
+    int issued = 0;
+    TrsmPanels(const AbstractDistMatrix<F>& L_, Dist pU, Dist pV, bool wantOverlap)
+        : L(L_), g(L_.Grid()), overlap(wantOverlap && dev::OverlapEnabled()),
+          mainS(dev::stream()), panelS(overlap ? elb200::aux_stream(0) : dev::stream()),
+          L11{AbstractDistMatrix<F>(g, STAR, STAR), AbstractDistMatrix<F>(g, STAR, STAR)},
+          Lp{AbstractDistMatrix<F>(g, pU, pV), AbstractDistMatrix<F>(g, pU, pV)} {
+        if (overlap) { fork.Record(mainS); fork.Wait(panelS); }
+    }
+    // enqueue the panels of block (k, nb); (pi, pj, ph, pw) = the coupling panel of the triangle, aligned with `like`
+    void Issue(Int k, Int nb, Int pi, Int pj, Int ph, Int pw, const AbstractDistMatrix<F>& like) {
+        const int s = issued & 1;
+        dev::StreamScope onPanel(panelS);
+        if (overlap && issued >= 2) freed[s].Wait(panelS);
+        auto L11v = LockedView(L, k, k, nb, nb);
+        Copy(static_cast<const AbstractDistMatrix<F>&>(L11v), L11[s]);
+        if (ph > 0 && pw > 0) {
+            Lp[s].AlignWith(like);
+            auto Lv = LockedView(L, pi, pj, ph, pw);
+            Copy(static_cast<const AbstractDistMatrix<F>&>(Lv), Lp[s]);
         }
-        if (side == LEFT) {
-            // Trsm/LLN.hpp:18-70 (forward) / LLT.hpp:20-80 (backward) and the LUN/LUT mirrors
-            auto X1 = View(X, k, 0, nb, X.Width());
-            AbstractDistMatrix<F> X1_STAR_VR(g, STAR, VR), X1_STAR_MR(g, STAR, MR);
+        if (overlap) ready[s].Record(panelS);
+        ++issued;
+    }
+    void Acquire(int s) { if (overlap) ready[s].Wait(mainS); }
+    void Release(int s) { if (overlap) freed[s].Record(mainS); }
+    ~TrsmPanels() {
+        if (overlap) {
+            // the panel buffers are released in main-stream order: make sure the panel stream is done with them
+            dev::Event join;
+            join.Record(panelS);
+            join.Wait(mainS);
+        }
+    }
+};
+
+// LEFT solves, "Large" and "Medium" (Trsm/LLN.hpp:18-126, LLT.hpp:20-141 and the LUN / LUT mirrors): they differ
+// only in how the solved block row travels.  Large: X1[*,VR] (solve spread over all p processes) then gathered to
+// [*,MR]; Medium: X1^T[MR,*] (one transposing redistribution, solve on the right, no second gather).
+template <typename F>
+void TrsmLeft(UpperOrLower uplo, Orientation o, UnitOrNonUnit diag, const AbstractDistMatrix<F>& L,
+              AbstractDistMatrix<F>& X, int* singularFlag, bool medium) {
+    const Grid& g = X.Grid();
+    const Int mTri = L.Height(), bsize = Blocksize(), nrhs = X.Width();
+    const bool effLower = (uplo == LOWER) == (o == NORMAL);
+    const bool forward = effLower;
+    const Int nblk = (mTri + bsize - 1) / bsize;
+    TrsmPanels<F> panels(L, o == NORMAL ? MC : STAR, o == NORMAL ? STAR : MC, g.Size() > 1 && nblk > 2);
+    AbstractDistMatrix<F> X1_STAR_VR(g, STAR, VR), X1_STAR_MR(g, STAR, MR), X1T_MR_STAR(g, MR, STAR);
+    auto block = [&](Int step, Int& k, Int& nb, Int& r0, Int& rl) {
+        const Int kb = forward ? step : nblk - 1 - step;
+        k = kb * bsize;
+        nb = std::min(bsize, mTri - k);
+        r0 = forward ? k + nb : 0;            // the not-yet-solved part
+        rl = forward ? mTri - (k + nb) : k;
+    };
+    auto issue = [&](Int step) {
+        Int k, nb, r0, rl;
+        block(step, k, nb, r0, rl);
+        auto X2 = LockedView(static_cast<const AbstractDistMatrix<F>&>(X), r0, 0, rl, nrhs);
+        if (o == NORMAL) panels.Issue(k, nb, r0, k, rl, nb, X2);   // L(rest, blk)[MC,*]
+        else panels.Issue(k, nb, k, r0, nb, rl, X2);               // L(blk, rest)[*,MC]
+    };
+    issue(0);
+    for (Int step = 0; step < nblk; ++step) {
+        Int k, nb, r0, rl;
+        block(step, k, nb, r0, rl);
+        const int s = (int)(step & 1);
+        if (step + 1 < nblk) issue(step + 1);
+        auto X1 = View(X, k, 0, nb, nrhs);
+        panels.Acquire(s);
+        if (singularFlag && diag != UNIT) ScanDiagonal(panels.L11[s].LockedMatrix(), singularFlag, k);
+        const Orientation oX = medium ? (o == ADJOINT ? ADJOINT : TRANSPOSE) : NORMAL;
+        if (!medium) {
             Copy(static_cast<const AbstractDistMatrix<F>&>(X1), X1_STAR_VR);
-            LocalTrsm(LEFT, uplo, o, diag, F(1), L11, X1_STAR_VR, checkIfSingular);
+            LocalTrsmRaw(LEFT, uplo, o, diag, F(1), panels.L11[s].LockedMatrix(), X1_STAR_VR.Matrix());
             if (rl > 0) {
-                auto X2 = View(X, r0, 0, rl, X.Width());
+                auto X2 = View(X, r0, 0, rl, nrhs);
                 X1_STAR_MR.AlignWith(X2);
                 Copy(static_cast<const AbstractDistMatrix<F>&>(X1_STAR_VR), X1_STAR_MR);
                 Copy(static_cast<const AbstractDistMatrix<F>&>(X1_STAR_MR), X1);
-                if (o == NORMAL) {
-                    AbstractDistMatrix<F> Lp(g, MC, STAR);
-                    Lp.AlignWith(X2);
-                    auto Lv = LockedView(L, r0, k, rl, nb);
-                    Copy(static_cast<const AbstractDistMatrix<F>&>(Lv), Lp);
-                    LocalGemm(NORMAL, NORMAL, F(-1), Lp, X1_STAR_MR, F(1), X2);
-                } else {
-                    AbstractDistMatrix<F> Lp(g, STAR, MC);
-                    Lp.AlignWith(X2);
-                    auto Lv = LockedView(L, k, r0, nb, rl);
-                    Copy(static_cast<const AbstractDistMatrix<F>&>(Lv), Lp);
-                    LocalGemm(o, NORMAL, F(-1), Lp, X1_STAR_MR, F(1), X2);
-                }
             } else {
                 Copy(static_cast<const AbstractDistMatrix<F>&>(X1_STAR_VR), X1);
             }
         } else {
-            // Trsm/RLN.hpp, RLT.hpp, RUN.hpp, RUT.hpp
-            auto X1 = View(X, 0, k, X.Height(), nb);
-            AbstractDistMatrix<F> X1_VC_STAR(g, VC, STAR), X1_MC_STAR(g, MC, STAR);
-            Copy(static_cast<const AbstractDistMatrix<F>&>(X1), X1_VC_STAR);
-            LocalTrsm(RIGHT, uplo, o, diag, F(1), L11, X1_VC_STAR, checkIfSingular);
+            // X1^[T/H][MR,*] := X1^[T/H][MR,*] op'(L11)^-1, op' = transpose for NORMAL, identity otherwise
+            X1T_MR_STAR.AlignWith(X);
+            Transpose(static_cast<const AbstractDistMatrix<F>&>(X1), X1T_MR_STAR, o == ADJOINT);
+            LocalTrsmRaw(RIGHT, uplo, o == NORMAL ? TRANSPOSE : NORMAL, diag, F(1), panels.L11[s].LockedMatrix(),
+                         X1T_MR_STAR.Matrix());
+            Transpose(static_cast<const AbstractDistMatrix<F>&>(X1T_MR_STAR), X1, o == ADJOINT);
+        }
+        if (rl > 0) {
+            auto X2 = View(X, r0, 0, rl, nrhs);
+            const AbstractDistMatrix<F>& Xrep = medium ? X1T_MR_STAR : X1_STAR_MR;
+            LocalGemm(o == NORMAL ? NORMAL : o, oX, F(-1), panels.Lp[s], Xrep, F(1), X2);
+        }
+        panels.Release(s);
+    }
+}
+
+// LEFT, "Small" (width(X) << p; LLN.hpp:129-175, LLT.hpp:144-252): triangle and right-hand sides both [VC,*], no
+// communication in the updates.  NORMAL: solve a block, update the rest (right-looking).  (Conjugate-)transposed:
+// the block first receives A(rest, blk)^[T/H] X(rest) -- partial sums on every process, summed over all of them --
+// and is then solved (left-looking).
+template <typename F>
+void TrsmLeftSmall(UpperOrLower uplo, Orientation o, UnitOrNonUnit diag, const AbstractDistMatrix<F>& APre,
+                   AbstractDistMatrix<F>& XPre, int* singularFlag) {
+    const Grid& g = XPre.Grid();
+    AbstractDistMatrix<F> A(g, VC, STAR), X(g, VC, STAR);
+    Copy(APre, A);
+    X.AlignCols(A.ColAlign());
+    Copy(static_cast<const AbstractDistMatrix<F>&>(XPre), X);
+    const Int mTri = A.Height(), bsize = Blocksize(), nrhs = X.Width();
+    const bool forward = (uplo == LOWER) == (o == NORMAL);
+    const Int nblk = (mTri + bsize - 1) / bsize;
+    AbstractDistMatrix<F> A11(g, STAR, STAR), X1s(g, STAR, STAR), Z1(g, STAR, STAR);
+    for (Int step = 0; step < nblk; ++step) {
+        const Int kb = forward ? step : nblk - 1 - step;
+        const Int k = kb * bsize, nb = std::min(bsize, mTri - k);
+        const Int r0 = forward ? k + nb : 0, rl = forward ? mTri - (k + nb) : k;       // not yet solved
+        const Int d0 = forward ? 0 : k + nb, dl = forward ? k : mTri - (k + nb);       // already solved
+        auto A11v = LockedView(static_cast<const AbstractDistMatrix<F>&>(A), k, k, nb, nb);
+        Copy(static_cast<const AbstractDistMatrix<F>&>(A11v), A11);
+        if (singularFlag && diag != UNIT) ScanDiagonal(A11.LockedMatrix(), singularFlag, k);
+        auto X1 = View(X, k, 0, nb, nrhs);
+        if (o == NORMAL) {
+            Copy(static_cast<const AbstractDistMatrix<F>&>(X1), X1s);
+            LocalTrsmRaw(LEFT, uplo, o, diag, F(1), A11.LockedMatrix(), X1s.Matrix());
+            Copy(static_cast<const AbstractDistMatrix<F>&>(X1s), X1);
             if (rl > 0) {
-                auto X2 = View(X, 0, r0, X.Height(), rl);
-                X1_MC_STAR.AlignWith(X2);
-                Copy(static_cast<const AbstractDistMatrix<F>&>(X1_VC_STAR), X1_MC_STAR);
-                Copy(static_cast<const AbstractDistMatrix<F>&>(X1_MC_STAR), X1);
-                if (o == NORMAL) {
-                    AbstractDistMatrix<F> Lp(g, STAR, MR);
-                    Lp.AlignWith(X2);
-                    auto Lv = LockedView(L, k, r0, nb, rl);
-                    Copy(static_cast<const AbstractDistMatrix<F>&>(Lv), Lp);
-                    LocalGemm(NORMAL, NORMAL, F(-1), X1_MC_STAR, Lp, F(1), X2);
-                } else {
-                    AbstractDistMatrix<F> Lp(g, MR, STAR);
-                    Lp.AlignWith(X2);
-                    auto Lv = LockedView(L, r0, k, rl, nb);
-                    Copy(static_cast<const AbstractDistMatrix<F>&>(Lv), Lp);
-                    LocalGemm(NORMAL, o, F(-1), X1_MC_STAR, Lp, F(1), X2);
-                }
-            } else {
-                Copy(static_cast<const AbstractDistMatrix<F>&>(X1_VC_STAR), X1);
+                auto A21 = LockedView(static_cast<const AbstractDistMatrix<F>&>(A), r0, k, rl, nb);
+                auto X2 = View(X, r0, 0, rl, nrhs);
+                LocalGemm(NORMAL, NORMAL, F(-1), A21, X1s, F(1), X2);
             }
+        } else {
+            if (dl > 0) {
+                auto Ad1 = LockedView(static_cast<const AbstractDistMatrix<F>&>(A), d0, k, dl, nb);
+                auto Xd = LockedView(static_cast<const AbstractDistMatrix<F>&>(X), d0, 0, dl, nrhs);
+                Z1.Resize(nb, nrhs);
+                LocalGemm(o, NORMAL, F(-1), Ad1, Xd, F(0), Z1);
+                AxpyContract(F(1), static_cast<const AbstractDistMatrix<F>&>(Z1), X1);   // X1 += sum over processes
+            }
+            Copy(static_cast<const AbstractDistMatrix<F>&>(X1), X1s);
+            LocalTrsmRaw(LEFT, uplo, o, diag, F(1), A11.LockedMatrix(), X1s.Matrix());
+            Copy(static_cast<const AbstractDistMatrix<F>&>(X1s), X1);
+            (void)rl; (void)r0;
         }
     }
-    XP.Commit();
+    Copy(static_cast<const AbstractDistMatrix<F>&>(X), XPre);
+}
+
+// RIGHT solves (Trsm/RLN.hpp, RLT.hpp, RUN.hpp, RUT.hpp)
+template <typename F>
+void TrsmRight(UpperOrLower uplo, Orientation o, UnitOrNonUnit diag, const AbstractDistMatrix<F>& L,
+               AbstractDistMatrix<F>& X, int* singularFlag) {
+    const Grid& g = X.Grid();
+    const Int mTri = L.Height(), bsize = Blocksize(), xm = X.Height();
+    const bool effLower = (uplo == LOWER) == (o == NORMAL);
+    const bool forward = !effLower;
+    const Int nblk = (mTri + bsize - 1) / bsize;
+    TrsmPanels<F> panels(L, o == NORMAL ? STAR : MR, o == NORMAL ? MR : STAR, g.Size() > 1 && nblk > 2);
+    AbstractDistMatrix<F> X1_VC_STAR(g, VC, STAR), X1_MC_STAR(g, MC, STAR);
+    auto block = [&](Int step, Int& k, Int& nb, Int& r0, Int& rl) {
+        const Int kb = forward ? step : nblk - 1 - step;
+        k = kb * bsize;
+        nb = std::min(bsize, mTri - k);
+        r0 = forward ? k + nb : 0;
+        rl = forward ? mTri - (k + nb) : k;
+    };
+    auto issue = [&](Int step) {
+        Int k, nb, r0, rl;
+        block(step, k, nb, r0, rl);
+        auto X2 = LockedView(static_cast<const AbstractDistMatrix<F>&>(X), 0, r0, xm, rl);
+        if (o == NORMAL) panels.Issue(k, nb, k, r0, nb, rl, X2);   // L(blk, rest)[*,MR]
+        else panels.Issue(k, nb, r0, k, rl, nb, X2);               // L(rest, blk)[MR,*]
+    };
+    issue(0);
+    for (Int step = 0; step < nblk; ++step) {
+        Int k, nb, r0, rl;
+        block(step, k, nb, r0, rl);
+        const int s = (int)(step & 1);
+        if (step + 1 < nblk) issue(step + 1);
+        auto X1 = View(X, 0, k, xm, nb);
+        panels.Acquire(s);
+        if (singularFlag && diag != UNIT) ScanDiagonal(panels.L11[s].LockedMatrix(), singularFlag, k);
+        Copy(static_cast<const AbstractDistMatrix<F>&>(X1), X1_VC_STAR);
+        LocalTrsmRaw(RIGHT, uplo, o, diag, F(1), panels.L11[s].LockedMatrix(), X1_VC_STAR.Matrix());
+        if (rl > 0) {
+            auto X2 = View(X, 0, r0, xm, rl);
+            X1_MC_STAR.AlignWith(X2);
+            Copy(static_cast<const AbstractDistMatrix<F>&>(X1_VC_STAR), X1_MC_STAR);
+            Copy(static_cast<const AbstractDistMatrix<F>&>(X1_MC_STAR), X1);
+            LocalGemm(NORMAL, o == NORMAL ? NORMAL : o, F(-1), X1_MC_STAR, panels.Lp[s], F(1), X2);
+        } else {
+            Copy(static_cast<const AbstractDistMatrix<F>&>(X1_VC_STAR), X1);
+        }
+        panels.Release(s);
+    }
+}
+
+}  // namespace
+
+// x := op(tri(A))^-1 x for a single column (src/blas_like/level2/Trsv.cpp:47-68, Trsv/{LN,LT,UN,UT}.hpp).  The
+// reference accumulates the updates in a [MC,*] / [*,MC] vector and reduces them block by block; here the column
+// runs through the Medium block substitution (its x1 is replicated as x1^T[MR,*], the update is a local
+// matrix-vector product on the tensor pipe) -- the same arithmetic per block, one code path.
+template <typename F>
+void Trsv(UpperOrLower uplo, Orientation o, UnitOrNonUnit diag, const AbstractDistMatrix<F>& APre,
+          AbstractDistMatrix<F>& xPre) {
+    AssertSameGrid(APre, xPre);
+    if (APre.Height() != APre.Width()) LogicError("A must be square");
+    if (xPre.Width() != 1 && xPre.Height() != 1) LogicError("x must be a vector");
+    const bool column = xPre.Width() == 1;
+    if ((column ? xPre.Height() : xPre.Width()) != APre.Height()) LogicError("x must conform with A");
+    ReadProxy<F> AP(APre);
+    if (column) {
+        ReadWriteProxy<F> XP(xPre);
+        TrsmLeft(uplo, o, diag, AP.Get(), XP.Get(), nullptr, true);
+        XP.Commit();
+    } else {
+        // a row vector: solve for its transpose
+        AbstractDistMatrix<F> xt(xPre.Grid(), MC, MR);
+        Transpose(static_cast<const AbstractDistMatrix<F>&>(xPre), xt, false);
+        TrsmLeft(uplo, o, diag, AP.Get(), xt, nullptr, true);
+        Transpose(static_cast<const AbstractDistMatrix<F>&>(xt), xPre, false);
+    }
+}
+
+// Algorithm selection as Trsm.cpp:94-375: width-1 left solves go to Trsv; LEFT: Large when width(B) > 5 p, else
+// Medium, Small only on request; RIGHT: the default algorithm only.
+template <typename F>
+void Trsm(LeftOrRight side, UpperOrLower uplo, Orientation o, UnitOrNonUnit diag, F alpha,
+          const AbstractDistMatrix<F>& APre, AbstractDistMatrix<F>& BPre, bool checkIfSingular, TrsmAlgorithm alg) {
+    AssertSameGrid(APre, BPre);
+    if (APre.Height() != APre.Width()) LogicError("A must be square");
+    if ((side == LEFT ? BPre.Height() : BPre.Width()) != APre.Height()) LogicError("Nonconformal Trsm");
+    if (side == RIGHT && alg != TRSM_DEFAULT) LogicError("Unsupported TRSM algorithm");
+    Scale(alpha, BPre);  // Trsm.cpp:94
+    if (APre.Height() == 0 || BPre.Height() == 0 || BPre.Width() == 0) return;
+    if (side == LEFT && BPre.Width() == 1 && !checkIfSingular) {
+        Trsv(uplo, o, diag, APre, BPre);   // Trsm.cpp:97-101
+        return;
+    }
+    std::unique_ptr<dev::DeviceFlag> flag;
+    if (checkIfSingular && diag != UNIT) flag.reset(new dev::DeviceFlag());
+    int* fdev = flag ? flag->dev_ : nullptr;
+    const Int p = BPre.Grid().Size();
+    if (side == LEFT && alg == TRSM_SMALL) {
+        TrsmLeftSmall(uplo, o, diag, APre, BPre, fdev);
+    } else {
+        ReadProxy<F> AP(APre);
+        ReadWriteProxy<F> XP(BPre);
+        if (side == LEFT) {
+            const bool medium = (alg == TRSM_MEDIUM) || (alg == TRSM_DEFAULT && !(BPre.Width() > 5 * p));
+            TrsmLeft(uplo, o, diag, AP.Get(), XP.Get(), fdev, medium);
+        } else {
+            TrsmRight(uplo, o, diag, AP.Get(), XP.Get(), fdev);
+        }
+        XP.Commit();
+    }
+    // the diagonal blocks are replicated, so every process reads the same flag (no deadlock); the reference throws
+    // at the first zero diagonal entry, before that block is solved (Trsm.cpp:54-60)
+    if (flag && flag->Read() != 0) throw SingularMatrixException();
 }
 
 #define ELB_INST(T)                                                                                                  \
@@ -658,6 +851,8 @@ void Trsm(LeftOrRight side, UpperOrLower uplo, Orientation o, UnitOrNonUnit diag
     template void Trsm(LeftOrRight, UpperOrLower, Orientation, UnitOrNonUnit, T, const Matrix<T>&, Matrix<T>&, bool); \
     template void Trsm(LeftOrRight, UpperOrLower, Orientation, UnitOrNonUnit, T, const AbstractDistMatrix<T>&,       \
                        AbstractDistMatrix<T>&, bool, TrsmAlgorithm);                                                 \
+    template void Trsv(UpperOrLower, Orientation, UnitOrNonUnit, const AbstractDistMatrix<T>&,                       \
+                       AbstractDistMatrix<T>&);                                                                      \
     template void LocalTrsm(LeftOrRight, UpperOrLower, Orientation, UnitOrNonUnit, T, const AbstractDistMatrix<T>&,  \
                             AbstractDistMatrix<T>&, bool);
 ELB_INST(float)

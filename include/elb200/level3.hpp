@@ -102,5 +102,9 @@ void Trsm(LeftOrRight side, UpperOrLower uplo, Orientation orientation, UnitOrNo
 template <typename F>
 void LocalTrsm(LeftOrRight side, UpperOrLower uplo, Orientation orientation, UnitOrNonUnit diag, F alpha,
                const AbstractDistMatrix<F>& A, AbstractDistMatrix<F>& X, bool checkIfSingular = false);
+// single right-hand side (src/blas_like/level2/Trsv.cpp:47-68); Trsm(LEFT, ...) dispatches here for width 1
+template <typename F>
+void Trsv(UpperOrLower uplo, Orientation orientation, UnitOrNonUnit diag, const AbstractDistMatrix<F>& A,
+          AbstractDistMatrix<F>& x);
 
 }  // namespace El

@@ -26,6 +26,7 @@ extern "C" {
 #endif
 
 typedef int ElInt;
+typedef enum { EL_TRSM_DEFAULT = 0, EL_TRSM_LARGE = 1, EL_TRSM_MEDIUM = 2, EL_TRSM_SMALL = 3 } ElTrsmAlgorithm; /* enum TrsmAlgorithm, include/El/blas_like/level3.hpp:445-452 */
 typedef enum {
     EL_SUCCESS, EL_ALLOC_ERROR, EL_OUT_OF_BOUNDS_ERROR, EL_ARG_ERROR, EL_LOGIC_ERROR, EL_RUNTIME_ERROR,
     EL_NON_HPD_ERROR = 100, EL_SINGULAR_ERROR = 101, /* extensions: reference maps these to EL_RUNTIME_ERROR */
@@ -154,6 +155,14 @@ ElError ElRedistStats(uint64_t out[8], bool reset);
     ElError ElTrsmDist_##SUF(ElLeftOrRight side, ElUpperOrLower uplo, ElOrientation orientation,            \
                              ElUnitOrNonUnit diag, SCALAR alpha, ElConstDistMatrix_##SUF A,                 \
                              ElDistMatrix_##SUF B);                                                         \
+    /* El::Trsm with its two C++-only arguments (include/El/blas_like/level3.hpp:455-470): checkIfSingular throws  */ \
+    /* EL_SINGULAR_ERROR on a zero diagonal entry (Trsm.cpp:54-60); alg picks Large / Medium / Small (LEFT only)   */ \
+    ElError ElTrsmXDist_##SUF(ElLeftOrRight side, ElUpperOrLower uplo, ElOrientation orientation,           \
+                              ElUnitOrNonUnit diag, SCALAR alpha, ElConstDistMatrix_##SUF A,                \
+                              ElDistMatrix_##SUF B, bool checkIfSingular, ElTrsmAlgorithm alg);             \
+    /* El::Trsv (src/blas_like/level2/Trsv.cpp:47-68): x is n x 1 or 1 x n */                              \
+    ElError ElTrsvDist_##SUF(ElUpperOrLower uplo, ElOrientation orientation, ElUnitOrNonUnit diag,          \
+                             ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF x);                              \
     /* siblings over the same leaves (include/El/blas_like/level3.h:371-374 Symm, :477-480 Syr2k,           \
        :559-562 Trmm) */                                                                                    \
     ElError ElSymmDist_##SUF(ElLeftOrRight side, ElUpperOrLower uplo, SCALAR alpha, ElConstDistMatrix_##SUF A, \

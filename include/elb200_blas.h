@@ -239,6 +239,43 @@ void cherk_(const char* uplo, const char* trans, const int* n, const int* k, con
 void zherk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha,
             const elb200_c64* A, const int* lda, const double* beta, elb200_c64* C, const int* ldc);
 
+/* ---- level 1 / 2 leaves of the same boundary (device pointers; kernels/level12_abi.cu) ----
+ *   ?syr_ / ?her_  src/core/imports/blas/Syr.hpp:12-30,152-173 (rank-1 updates of the unblocked Cholesky)
+ *   ?scal_         Scal.hpp:12-19,118-125      ?axpy_  Axpy.hpp:12-29
+ *   ?lacpy_        src/core/imports/lapack.cpp:20-31,381-396 (uplo 'U' / 'L' / anything else = all) */
+int elb200_sscal(int64_t n, float alpha, float* x, int64_t incx, elb200_stream_t s);
+int elb200_dscal(int64_t n, double alpha, double* x, int64_t incx, elb200_stream_t s);
+int elb200_cscal(int64_t n, elb200_c32 alpha, elb200_c32* x, int64_t incx, elb200_stream_t s);
+int elb200_zscal(int64_t n, elb200_c64 alpha, elb200_c64* x, int64_t incx, elb200_stream_t s);
+int elb200_saxpy(int64_t n, float alpha, const float* x, int64_t incx, float* y, int64_t incy, elb200_stream_t s);
+int elb200_daxpy(int64_t n, double alpha, const double* x, int64_t incx, double* y, int64_t incy, elb200_stream_t s);
+int elb200_caxpy(int64_t n, elb200_c32 alpha, const elb200_c32* x, int64_t incx, elb200_c32* y, int64_t incy, elb200_stream_t s);
+int elb200_zaxpy(int64_t n, elb200_c64 alpha, const elb200_c64* x, int64_t incx, elb200_c64* y, int64_t incy, elb200_stream_t s);
+int elb200_slacpy(char uplo, int64_t m, int64_t n, const float* A, int64_t lda, float* B, int64_t ldb, elb200_stream_t s);
+int elb200_dlacpy(char uplo, int64_t m, int64_t n, const double* A, int64_t lda, double* B, int64_t ldb, elb200_stream_t s);
+int elb200_clacpy(char uplo, int64_t m, int64_t n, const elb200_c32* A, int64_t lda, elb200_c32* B, int64_t ldb, elb200_stream_t s);
+int elb200_zlacpy(char uplo, int64_t m, int64_t n, const elb200_c64* A, int64_t lda, elb200_c64* B, int64_t ldb, elb200_stream_t s);
+int elb200_ssyr(char uplo, int64_t n, float alpha, const float* x, int64_t incx, float* A, int64_t lda, elb200_stream_t s);
+int elb200_dsyr(char uplo, int64_t n, double alpha, const double* x, int64_t incx, double* A, int64_t lda, elb200_stream_t s);
+int elb200_cher(char uplo, int64_t n, float alpha, const elb200_c32* x, int64_t incx, elb200_c32* A, int64_t lda, elb200_stream_t s);
+int elb200_zher(char uplo, int64_t n, double alpha, const elb200_c64* x, int64_t incx, elb200_c64* A, int64_t lda, elb200_stream_t s);
+void sscal_(const int* n, const float* alpha, float* x, const int* incx);
+void dscal_(const int* n, const double* alpha, double* x, const int* incx);
+void cscal_(const int* n, const elb200_c32* alpha, elb200_c32* x, const int* incx);
+void zscal_(const int* n, const elb200_c64* alpha, elb200_c64* x, const int* incx);
+void saxpy_(const int* n, const float* alpha, const float* x, const int* incx, float* y, const int* incy);
+void daxpy_(const int* n, const double* alpha, const double* x, const int* incx, double* y, const int* incy);
+void caxpy_(const int* n, const elb200_c32* alpha, const elb200_c32* x, const int* incx, elb200_c32* y, const int* incy);
+void zaxpy_(const int* n, const elb200_c64* alpha, const elb200_c64* x, const int* incx, elb200_c64* y, const int* incy);
+void slacpy_(const char* uplo, const int* m, const int* n, const float* A, const int* lda, float* B, const int* ldb);
+void dlacpy_(const char* uplo, const int* m, const int* n, const double* A, const int* lda, double* B, const int* ldb);
+void clacpy_(const char* uplo, const int* m, const int* n, const elb200_c32* A, const int* lda, elb200_c32* B, const int* ldb);
+void zlacpy_(const char* uplo, const int* m, const int* n, const elb200_c64* A, const int* lda, elb200_c64* B, const int* ldb);
+void ssyr_(const char* uplo, const int* n, const float* alpha, const float* x, const int* incx, float* A, const int* lda);
+void dsyr_(const char* uplo, const int* n, const double* alpha, const double* x, const int* incx, double* A, const int* lda);
+void cher_(const char* uplo, const int* n, const float* alpha, const elb200_c32* x, const int* incx, elb200_c32* A, const int* lda);
+void zher_(const char* uplo, const int* n, const double* alpha, const elb200_c64* x, const int* incx, elb200_c64* A, const int* lda);
+
 #ifdef __cplusplus
 }
 #endif

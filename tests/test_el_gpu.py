@@ -17,6 +17,8 @@ from oracle import reference_lib as R
 pytestmark = pytest.mark.gpu
 
 DT = [np.float64, np.complex128, np.float32, np.complex64]
+UL = {"L": 0, "U": 1}
+DG = {"N": 0, "U": 1}
 ORI = {"N": 0, "T": 1, "C": 2}
 
 
@@ -208,7 +210,8 @@ def test_trsm_dist_all_variants(El, dt):
     m, n, nb = 150, 90, 32
     for side in "LR":
         na = m if side == "L" else n
-        A = O.fill(0, na, na, 9, dtype=dt) + na * np.eye(na)
+        # strict triangle scaled by 1/na: the unit-diagonal variants stay well conditioned too
+        A = O.fill(0, na, na, 9, dtype=dt) / na + 2 * np.eye(na)
         for uplo in "LU":
             for tr in "NTC":
                 for diag in "NU":
@@ -223,6 +226,106 @@ def test_trsm_dist_all_variants(El, dt):
                     lhs = opT @ X if side == "L" else X @ opT
                     e = np.finfo(np.float64).eps
                     assert np.linalg.norm(lhs - 2.0 * B0) <= 50 * na * e * np.linalg.norm(T) * np.linalg.norm(X), (side, uplo, tr, diag)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128])
+def test_trsm_dist_algorithms_and_trsv(El, dt):
+    """TrsmAlgorithm Large / Medium / Small (Trsm/LLN.hpp:18-175, LLT.hpp:20-252 and the upper mirrors), the default
+    rule (Large iff width > 5 p, Trsm.cpp:126-128), and the width-1 dispatch to Trsv (Trsm.cpp:97-101), against the
+    reference library at the same blocksize (residual-level: the reference's flops are an external BLAS)."""
+    m, nb = 150, 32
+    A = np.asfortranarray((O.fill(0, m, m, 9, dtype=dt) / m + 2 * np.eye(m)).astype(dt))
+    e = np.finfo(np.float64).eps
+    for n in (40, 4, 1):
+        for uplo in "LU":
+            for tr in "NTC":
+                for diag in "NU":
+                    B0 = O.fill(0, m, n, 10, dtype=dt)
+                    ref = (R.trsm("L", uplo, tr, diag, 2.0, A, B0.copy(order="F"), nb=nb) if R.available()
+                           else O.trsm("L", uplo, tr, diag, 2.0, A, B0.copy(order="F"), nb=nb))
+                    for alg in (El.TRSM_DEFAULT, El.TRSM_LARGE, El.TRSM_MEDIUM, El.TRSM_SMALL):
+                        dA, dB = _dm(El, A), _dm(El, B0)
+                        El.PushBlocksizeStack(nb)
+                        El.Trsm(0, UL[uplo], ORI[tr], DG[diag], 2.0, dA, dB, False, alg)
+                        El.PopBlocksizeStack()
+                        X = dB.ToGlobal()
+                        assert np.linalg.norm(X - ref) <= 50 * m * e * np.linalg.norm(ref), (dt, n, uplo, tr, diag, alg)
+    # El::Trsv on a column and on a row vector
+    for uplo in "LU":
+        for tr in "NC":
+            x0 = O.fill(0, m, 1, 12, dtype=dt)
+            T = O._tri(A, uplo, "N")
+            opT = T if tr == "N" else T.conj().T
+            want = np.linalg.solve(opT, x0)
+            dA, dx = _dm(El, A), _dm(El, x0)
+            El.Trsv(UL[uplo], ORI[tr], 0, dA, dx)
+            assert np.linalg.norm(dx.ToGlobal() - want) <= 50 * m * e * np.linalg.norm(want)
+            dr = _dm(El, np.asfortranarray(x0.T))
+            El.Trsv(UL[uplo], ORI[tr], 0, dA, dr)
+            assert np.linalg.norm(dr.ToGlobal().T - want) <= 50 * m * e * np.linalg.norm(want)
+
+
+def test_trsm_check_if_singular_raises(El):
+    """checkIfSingular: a zero on the diagonal raises SingularMatrixException (Trsm.cpp:54-60) -- from the
+    distributed solve (any block) and not for a unit-diagonal solve; without the flag inf/nan come out silently."""
+    m, n, nb = 100, 30, 32
+    A = np.asfortranarray(O.fill(0, m, m, 9) / m + 2 * np.eye(m))
+    A[70, 70] = 0.0
+    B0 = O.fill(0, m, n, 10)
+    for alg in (El.TRSM_LARGE, El.TRSM_MEDIUM, El.TRSM_SMALL):
+        dA, dB = _dm(El, A), _dm(El, B0)
+        El.PushBlocksizeStack(nb)
+        with pytest.raises(El.SingularMatrixException):
+            El.Trsm(0, 0, 0, 0, 1.0, dA, dB, True, alg)
+        dB = _dm(El, B0)
+        El.Trsm(0, 0, 0, 1, 1.0, dA, dB, True, alg)      # UNIT: the stored diagonal is never read
+        assert np.all(np.isfinite(dB.ToGlobal()))
+        El.PopBlocksizeStack()
+    dA, dB = _dm(El, A), _dm(El, np.asfortranarray(B0.T))
+    with pytest.raises(El.SingularMatrixException):
+        El.Trsm(1, 0, 0, 0, 1.0, dA, dB, True)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128, np.float32])
+def test_syrk_herk_trrk_dist_with_beta(El, dt):
+    """beta != 1 exercises ScaleTrapezoid on the local staircase (level1/ScaleTrapezoid.hpp:14-86) before the panel
+    loop; the strictly-other triangle must stay bit-identical."""
+    n, k, nb = 170, 90, 48
+    e = np.finfo(np.dtype(dt).type(0).real.dtype).eps
+    for uplo in "LU":
+        for o in "NC":
+            A = O.fill(0, *((n, k) if o == "N" else (k, n)), 3, dtype=dt)
+            C0 = O.fill(0, n, n, 4, dtype=dt)
+            mask = O._tri_mask(n, n, uplo)
+            El.SetBlocksize(nb)
+            dC = _dm(El, C0)
+            El.Herk(UL[uplo], ORI[o], -0.75, _dm(El, A), 0.5, dC)
+            ref = (R.herk(uplo, o, -0.75, A, 0.5, C0.copy(order="F"), nb=nb) if R.available() and dt != np.float32
+                   else O.herk(uplo, o, -0.75, A, 0.5, C0.copy(order="F")))   # the reference driver has no float herk
+            got = dC.ToGlobal()
+            assert np.array_equal(got[~mask], C0[~mask])
+            assert np.linalg.norm(got - ref) <= 4 * k * e * (np.linalg.norm(A) ** 2 + np.linalg.norm(C0))
+            dC = _dm(El, C0)
+            oo = "N" if o == "N" else "T"
+            El.Syrk(UL[uplo], ORI[oo], 1.5, _dm(El, A), -2.0, dC)
+            P = (A @ A.T) if o == "N" else (A.T @ A)
+            want = np.where(mask, 1.5 * P - 2.0 * C0, C0)
+            got = dC.ToGlobal()
+            assert np.array_equal(got[~mask], C0[~mask])
+            assert np.linalg.norm(got - want) <= 4 * k * e * (1.5 * np.linalg.norm(A) ** 2 + 2 * np.linalg.norm(C0))
+            for oa, ob in (("N", "N"), ("C", "N"), ("N", "T")):
+                if (oa == "N") != (o == "N"):
+                    continue
+                Bm = O.fill(0, *((k, n) if ob == "N" else (n, k)), 5, dtype=dt)
+                opA = A if oa == "N" else A.conj().T
+                opB = Bm if ob == "N" else Bm.T
+                dC = _dm(El, C0)
+                El.Trrk(UL[uplo], ORI[oa], ORI[ob], 2.0, _dm(El, A), _dm(El, Bm), 0.25, dC)
+                want = np.where(mask, 2.0 * (opA @ opB) + 0.25 * C0, C0)
+                got = dC.ToGlobal()
+                assert np.array_equal(got[~mask], C0[~mask])
+                assert np.linalg.norm(got - want) <= 4 * k * e * (2 * np.linalg.norm(A) * np.linalg.norm(Bm) + np.linalg.norm(C0))
+    El.SetBlocksize(128)
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.complex128])

@@ -84,7 +84,9 @@ def test_trsm_all_variants(dt):
     for (m, n) in [(100, 37), (33, 64), (1, 5), (70, 1), (256, 130)]:
         for side in "LR":
             na = m if side == "L" else n
-            A = G.rand(rng, na, na, dt) + na * np.eye(na, dtype=dt)
+            # strict triangle scaled by 1/na so that the unit-diagonal variants are well conditioned too (with
+            # O(1) off-diagonals they are exponentially ill-conditioned and ||X|| overflows in float)
+            A = G.rand(rng, na, na, dt) / max(na, 1) + 2 * np.eye(na, dtype=dt)
             for uplo in "LU":
                 for tr in "NTC":
                     for diag in "NU":
@@ -96,6 +98,7 @@ def test_trsm_all_variants(dt):
                         T = O._tri(A, uplo, diag)
                         lhs = _op(T, tr) @ X if side == "L" else X @ _op(T, tr)
                         res = np.linalg.norm(lhs - alpha * B0)
+                        assert np.all(np.isfinite(X))
                         assert res <= 50 * na * G.eps(dt) * np.linalg.norm(T) * max(np.linalg.norm(X), 1e-30), \
                             (dt, side, uplo, tr, diag, m, n, res)
                         assert dB.padding_untouched()
@@ -300,3 +303,168 @@ def test_sgemm_3xtf32_rejects_unaligned_operands_loudly():
     dA, dB, dC = G.DevMat(A, 65), G.DevMat(B, 64), G.DevMat(C0, 64)   # lda % 4 != 0
     with pytest.raises(Exception):
         G.gemm("N", "N", 1.0, dA, dB, 0.0, dC, 64, fn="elb200_sgemm_3xtf32")
+
+
+def test_trsm_alpha_zero_does_not_reference_a():
+    """alpha == 0: B := 0 without touching A (the BLAS definition), even when A holds NaN."""
+    import gpuutil as G
+    A = np.full((40, 40), np.nan)
+    B0 = np.asfortranarray(np.random.default_rng(1).uniform(-1, 1, (40, 17)))
+    B0[3, 4] = np.inf
+    dA, dB = G.DevMat(A), G.DevMat(B0, 42)
+    G.trsm("L", "L", "N", "N", 0.0, dA, dB)
+    assert np.array_equal(dB.get(), np.zeros_like(B0)) and dB.padding_untouched()
+
+
+def test_fortran_abi_level3_on_current_stream():
+    """The Fortran symbols the reference binds besides ?gemm_ (src/core/imports/blas/Trsm.hpp:12-33, Syrk.hpp:12-50):
+    dtrsm_, ztrsm_, dsyrk_, ssyrk_, zherk_, cherk_, zsyrk_ with by-reference scalars and device arrays."""
+    import ctypes as C
+    import torch
+    import gpuutil as G
+    from elemental_b200._lib import lib, c32, c64
+    L = lib()
+    L.elb200_set_stream(G.stream())
+    rng = np.random.default_rng(5)
+    i = lambda v: C.byref(C.c_int(v))
+    ch = lambda c: C.c_char_p(c.encode())
+    scal = {np.float32: lambda v: C.byref(C.c_float(v)), np.float64: lambda v: C.byref(C.c_double(v)),
+            np.complex64: lambda v: C.byref(c32(v.real, v.imag)), np.complex128: lambda v: C.byref(c64(v.real, v.imag))}
+    # ?trsm_
+    for dt, name in ((np.float64, "dtrsm_"), (np.complex128, "ztrsm_"), (np.float32, "strsm_"), (np.complex64, "ctrsm_")):
+        m, n = 70, 33
+        A = G.rand(rng, m, m, dt) / m + 2 * np.eye(m, dtype=dt)
+        B0 = G.rand(rng, m, n, dt)
+        dA, dB = G.DevMat(A, m + 2), G.DevMat(B0, m + 1)
+        alpha = dt(2.0) if dt in (np.float32, np.float64) else dt(2.0 - 1.0j)
+        getattr(L, name)(ch("L"), ch("U"), ch("C"), ch("N"), i(m), i(n), scal[dt](alpha), dA.ptr, i(dA.ld), dB.ptr, i(dB.ld))
+        torch.cuda.synchronize()
+        T = np.triu(A)
+        assert np.linalg.norm(T.conj().T @ dB.get() - alpha * B0) <= 50 * m * G.eps(dt) * np.linalg.norm(T) * np.linalg.norm(B0)
+    # ?syrk_ / ?herk_
+    n, k = 65, 40
+    for dt, name, herm in ((np.float64, "dsyrk_", False), (np.float32, "ssyrk_", False), (np.complex128, "zsyrk_", False),
+                           (np.complex128, "zherk_", True), (np.complex64, "cherk_", True)):
+        A = G.rand(rng, n, k, dt)
+        C0 = G.rand(rng, n, n, dt)
+        if herm:
+            C0 = C0 + C0.conj().T
+        dA, dC = G.DevMat(A, n + 1), G.DevMat(C0, n + 3)
+        rdt = np.float32 if dt in (np.float32, np.complex64) else np.float64
+        if herm:
+            a, b = rdt(-1.5), rdt(0.5)
+            getattr(L, name)(ch("L"), ch("N"), i(n), i(k), scal[rdt](a), dA.ptr, i(dA.ld), scal[rdt](b), dC.ptr, i(dC.ld))
+            P = A @ A.conj().T
+        else:
+            a, b = dt(-1.5), dt(0.5)
+            getattr(L, name)(ch("L"), ch("N"), i(n), i(k), scal[dt](a), dA.ptr, i(dA.ld), scal[dt](b), dC.ptr, i(dC.ld))
+            P = A @ A.T
+        torch.cuda.synchronize()
+        got = dC.get()
+        low = np.tril(np.ones((n, n), bool))
+        want = np.where(low, a * P + b * C0, C0)
+        assert np.array_equal(got[~low], C0[~low]), name
+        assert np.linalg.norm(got - want) <= 8 * k * G.eps(dt) * (np.linalg.norm(A) ** 2 + np.linalg.norm(C0)), name
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_fortran_abi_level1_level2(dt):
+    """?scal_, ?axpy_, ?lacpy_, ?syr_ / ?her_ (src/core/imports/blas/Scal.hpp:12-19, Axpy.hpp:12-29, Syr.hpp:12-30,
+    src/core/imports/lapack.cpp:20-31) as device kernels: bit-exact against numpy for the copies, rounding-level
+    for the arithmetic; strided and negative increments as BLAS defines them."""
+    import ctypes as C
+    import torch
+    import gpuutil as G
+    from elemental_b200._lib import lib, c32, c64
+    L = lib()
+    L.elb200_set_stream(G.stream())
+    rng = np.random.default_rng(6)
+    p = G.SUF[np.dtype(dt)]
+    cplx = np.dtype(dt).kind == "c"
+    rdt = np.float32 if np.dtype(dt) in (np.dtype(np.float32), np.dtype(np.complex64)) else np.float64
+    i = lambda v: C.byref(C.c_int(v))
+    ch = lambda c: C.c_char_p(c.encode())
+    def sc(v):
+        if np.dtype(dt) == np.float32: return C.byref(C.c_float(v))
+        if np.dtype(dt) == np.float64: return C.byref(C.c_double(v))
+        return C.byref((c32 if np.dtype(dt) == np.complex64 else c64)(complex(v).real, complex(v).imag))
+    alpha = dt(1.5 - 0.5j) if cplx else dt(1.5)
+    e = G.eps(dt)
+    n = 1000
+    for incx, incy in ((1, 1), (3, 2), (-2, 1)):
+        x = G.rand(rng, n * abs(incx), 1, dt)[:, 0]
+        y = G.rand(rng, n * abs(incy), 1, dt)[:, 0]
+        tx, ty = torch.from_numpy(x.copy()).cuda(), torch.from_numpy(y.copy()).cuda()
+        getattr(L, p + "axpy_")(i(n), sc(alpha), C.c_void_p(tx.data_ptr()), i(incx), C.c_void_p(ty.data_ptr()), i(incy))
+        torch.cuda.synchronize()
+        xs = x[::incx][:n] if incx > 0 else x[: (n - 1) * (-incx) + 1][::-1][::-incx][:n]
+        want = y.copy()
+        idx = np.arange(n) * incy
+        want[idx] = y[idx] + alpha * xs
+        assert np.linalg.norm(ty.cpu().numpy() - want) <= 4 * e * np.linalg.norm(want)
+        if incx > 0:
+            getattr(L, p + "scal_")(i(n), sc(alpha), C.c_void_p(tx.data_ptr()), i(incx))
+            torch.cuda.synchronize()
+            want = x.copy()
+            want[np.arange(n) * incx] = alpha * x[np.arange(n) * incx]
+            assert np.linalg.norm(tx.cpu().numpy() - want) <= 4 * e * np.linalg.norm(want)
+    m, nn = 45, 37
+    A = G.rand(rng, m, nn, dt)
+    for uplo in "ULA":
+        B0 = G.rand(rng, m, nn, dt)
+        dA, dB = G.DevMat(A, m + 3), G.DevMat(B0, m + 1)
+        getattr(L, p + "lacpy_")(ch(uplo), i(m), i(nn), dA.ptr, i(dA.ld), dB.ptr, i(dB.ld))
+        torch.cuda.synchronize()
+        ii, jj = np.indices((m, nn))
+        sel = (ii <= jj) if uplo == "U" else ((ii >= jj) if uplo == "L" else np.ones((m, nn), bool))
+        assert np.array_equal(dB.get(), np.where(sel, A, B0)) and dB.padding_untouched()
+    nn = 130
+    x = G.rand(rng, nn, 1, dt)[:, 0]
+    tx = torch.from_numpy(x.copy()).cuda()
+    name = {"s": "ssyr_", "d": "dsyr_", "c": "cher_", "z": "zher_"}[p]
+    for uplo in "LU":
+        A0 = G.rand(rng, nn, nn, dt)
+        dA = G.DevMat(A0, nn + 1)
+        ra = rdt(-0.75)
+        ralpha = C.byref(C.c_float(ra)) if rdt == np.float32 else C.byref(C.c_double(ra))
+        getattr(L, name)(ch(uplo), i(nn), ralpha, C.c_void_p(tx.data_ptr()), i(1), dA.ptr, i(dA.ld))
+        torch.cuda.synchronize()
+        ii, jj = np.indices((nn, nn))
+        tri = (ii >= jj) if uplo == "L" else (ii <= jj)
+        upd = A0 + ra * np.outer(x, x.conj() if cplx else x)
+        if cplx:
+            upd[np.arange(nn), np.arange(nn)] = upd[np.arange(nn), np.arange(nn)].real
+        want = np.where(tri, upd, A0)
+        got = dA.get()
+        assert np.array_equal(got[~tri], A0[~tri]) and dA.padding_untouched()
+        assert np.linalg.norm(got - want) <= 8 * e * np.linalg.norm(want)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_trapezoid_kernels_on_the_global_staircase(dt):
+    """elb200_scale_trapezoid / elb200_make_trapezoidal (ScaleTrapezoid.hpp:14-86, MakeTrapezoidal) with alpha != 1,
+    nonzero offsets and [MC,MR]-style shifts / strides: bit-exact against the same predicate in numpy."""
+    import ctypes as C
+    import gpuutil as G
+    from elemental_b200._lib import lib, check
+    L = lib()
+    rng = np.random.default_rng(8)
+    m, n = 77, 53
+    code = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.complex64): 2, np.dtype(np.complex128): 3}[np.dtype(dt)]
+    alpha = dt(0.5)   # a power of two: the scaled entries are exact
+    for (rs, rst, cs, cst) in ((0, 1, 0, 1), (1, 2, 3, 4), (2, 3, 0, 2)):
+        for uplo in "LU":
+            for off in (0, 1, -2, 5):
+                A0 = G.rand(rng, m, n, dt)
+                gi = rs + np.arange(m)[:, None] * rst
+                gj = cs + np.arange(n)[None, :] * cst
+                inside = (gj - gi <= off) if uplo == "L" else (gj - gi >= off)
+                dA = G.DevMat(A0, m + 1)
+                a = G.sc(dt, alpha)
+                check(L.elb200_scale_trapezoid(code, C.byref(a), G.ch(uplo), G.i64(m), G.i64(n), dA.ptr, G.i64(dA.ld),
+                                               G.i64(rs), G.i64(rst), G.i64(cs), G.i64(cst), G.i64(off), G.stream()), "scale")
+                assert np.array_equal(dA.get(), np.where(inside, alpha * A0, A0)) and dA.padding_untouched()
+                dA = G.DevMat(A0, m + 1)
+                check(L.elb200_make_trapezoidal(code, G.ch(uplo), G.i64(m), G.i64(n), dA.ptr, G.i64(dA.ld),
+                                                G.i64(rs), G.i64(rst), G.i64(cs), G.i64(cst), G.i64(off), G.stream()), "make")
+                assert np.array_equal(dA.get(), np.where(inside, A0, 0)) and dA.padding_untouched()
