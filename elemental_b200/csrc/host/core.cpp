@@ -200,8 +200,10 @@ Grid::Grid(const void* uid, int worldRank, int worldSize, int height, GridOrder 
 // Allocate this rank's exchange window, publish its IPC handle through one ncclAllGather and map the
 // windows of all peers.  Collective: the path is enabled only if EVERY rank succeeded.
 void Grid::SetupP2P(int worldSize) {
+    // on by default since round 2 (parity suite green on 1x2, 2x1, 2x2 and 2x4); ELB200_P2P=0 keeps every wire
+    // step on ncclSend / ncclRecv
     const char* e = std::getenv("ELB200_P2P");
-    if (!e || std::atoi(e) == 0 || worldSize > elb200::P2P_MAX_PEERS) return;
+    if ((e && std::atoi(e) == 0) || worldSize > elb200::P2P_MAX_PEERS) return;
     const char* r = std::getenv("ELB200_P2P_REGION_MB");
     const size_t regionBytes = (size_t)(r ? std::max(1, std::atoi(r)) : 64) << 20;
     const size_t bytes = 4096 + (size_t)4 * worldSize * regionBytes;
@@ -243,7 +245,7 @@ void Grid::SetupP2P(int worldSize) {
         for (int w = 0; w < worldSize; ++w)
             if (w != worldRank_ && peer[w]) cudaIpcCloseMemHandle(peer[w]);
         if (local) cudaFree(local);
-        if (worldRank_ == 0) std::fprintf(stderr, "[elb200] ELB200_P2P=1 but the exchange windows could not be mapped; using NCCL\n");
+        if (worldRank_ == 0 && e) std::fprintf(stderr, "[elb200] ELB200_P2P=1 but the exchange windows could not be mapped; using NCCL\n");
         return;
     }
     p2p_.regionBytes = regionBytes;

@@ -12,6 +12,7 @@
 //              Trrk.cpp:100-116 + Trrk/*.hpp, Syrk.cpp:70-86 + Syrk/*.hpp, Herk.cpp,
 //              Trsm.cpp:67-375 + Trsm/{LLN,LLT,LUN,LUT,RLN,RLT,RUN,RUT}.hpp
 #include <algorithm>
+#include <cstdlib>
 #include <memory>
 
 #include "dev.hpp"
@@ -171,8 +172,12 @@ void SummaC(Orientation oA, Orientation oB, T alpha, const AbstractDistMatrix<T>
         return;
     }
     cudaStream_t mainS = dev::stream(), panelS = elb200::aux_stream(0);
-    const int reserve = dev::PanelSms(8);
-    const int gemmSms = std::max(1, elb200::sm_count() - reserve);
+    // SMs left to the gather kernels of the panel stream: 8 for NCCL's send / recv kernels, none with the
+    // peer-memory path (the wire step runs on the copy engines; the short unpack kernels of the high-priority panel
+    // stream slip in between two updates).  Measured at N = 2: 63.9 -> 67.3 TFLOP/s.  ELB200_SUMMA_PANEL_SMS overrides.
+    int reserve = g.P2P().on ? 0 : dev::PanelSms(8);
+    if (const char* e = std::getenv("ELB200_SUMMA_PANEL_SMS")) reserve = std::atoi(e);
+    const int gemmSms = reserve > 0 ? std::max(1, elb200::sm_count() - reserve) : 0;
     AbstractDistMatrix<T> A1[2] = {AbstractDistMatrix<T>(g, MC, STAR), AbstractDistMatrix<T>(g, MC, STAR)};
     AbstractDistMatrix<T> B1[2] = {AbstractDistMatrix<T>(g, STAR, MR), AbstractDistMatrix<T>(g, STAR, MR)};
     dev::Event ready[2], freed[2], fork;
