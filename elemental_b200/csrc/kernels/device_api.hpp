@@ -68,6 +68,7 @@ struct P2PFlagOps {
     int* error;  // pinned host memory: set when a wait times out
 };
 void p2p_flags(const P2PFlagOps& ops, cudaStream_t s);
+int p2p_flag_mode();  // 1: stream memory operations (no kernel), 0: one-warp flag kernel
 void scratch_free(void* p, cudaStream_t s);
 
 template <class T> struct dtype_code;

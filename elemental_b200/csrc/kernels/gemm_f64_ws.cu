@@ -66,7 +66,8 @@ constexpr int RING_BYTES = STAGES * STAGE_BYTES;
 constexpr int INFO_SLOTS = 8;      // > STAGES + 1: a slot is rewritten only after its tile's epilogue started
 constexpr int BAR_BYTES = GROUPS * 2 * STAGES * 8;
 constexpr int INFO_BYTES = GROUPS * INFO_SLOTS * 16;
-constexpr int PST_BYTES = GROUPS * 32;  // producer cursors
+constexpr int PST_BYTES = GROUPS * 64;  // producer cursors
+constexpr unsigned TILE_CHUNK = 4;     // tiles per atomicAdd on the tile counter
 constexpr int SMEM_BYTES = GROUPS * RING_BYTES + 1024 /*alignment slack*/ + BAR_BYTES + INFO_BYTES + PST_BYTES;
 constexpr int GROUP_N = 16;        // tile columns per rasterisation band (in 64-column tiles)
 
@@ -84,6 +85,7 @@ struct WsArgs {
     int alphaMode;    // 0: general, 1: alpha == 1, 2: alpha == -1
     int bandw;        // tile columns per rasterisation band
     unsigned staggerNs;  // group 1 starts this much later than group 0
+    unsigned* tileCounter;  // zeroed before the launch: tiles are handed out in raster order, TILE_CHUNK at a time
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -330,24 +332,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_ws_kernel(const __grid_c
     const unsigned full0 = bars + (group * 2 * STAGES) * 8;
     const unsigned empty0 = full0 + STAGES * 8;
     const unsigned info0 = infos + group * INFO_SLOTS * 16;
-    const unsigned pst0 = psts + group * 32;
+    const unsigned pst0 = psts + group * 64;
     const int KT = (int)((p.k + BK - 1) / BK);
 
     // ---- producer (warp 0 of the group).  Its cursor {tile, row0, col0, class | k-stage, ring slot, phase, tile
     //      sequence number} lives in SHARED memory: kept in registers it would be live across the k loop of
     //      every warp, and the compiler then recomputes the fragment addresses at each k-step instead ----
-    // next tile of this group at or after `from` that has work (total when there is none)
-    auto seek = [&](unsigned from, int& m0, int& n0, int& cls) -> unsigned {
+    // Next tile with work, drawn from the launch-wide tile counter (all CTAs and both groups share it, so the tile
+    // order is the raster order and nobody is left with more than a few tiles more than anybody else: with the
+    // static round-robin of the previous versions the staircase of a TRRK left some CTAs up to 12 % more tiles).
+    // `cur` / `end` are the unconsumed part of the chunk this warp holds.  Returns total when nothing is left.
+    // Runs on all lanes of warp 0 (lane 0 does the atomic).
+    auto seek = [&](unsigned& cur, unsigned& end, int& m0, int& n0, int& cls) -> unsigned {
         const unsigned total = (unsigned)(p.tilesM * p.tilesN);
-        const unsigned tstep = gridDim.x * GROUPS;
-        unsigned tl = from;
-        for (; tl < total; tl += tstep) {
+        for (;;) {
+            if (cur >= end) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(p.tileCounter, TILE_CHUNK);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= total) { cur = end = total; return total; }
+                cur = base;
+                end = (base + TILE_CHUNK < total) ? base + TILE_CHUNK : total;
+            }
+            const unsigned tl = cur++;
             unsigned tm, tn;
             tile_coords(p, tl, tm, tn);
             const int c = tile_class<MODE>(p, (i64)tm * TM, (i64)tn * TN);
-            if (c != 0) { m0 = (int)(tm * TM); n0 = (int)(tn * TN); cls = c; break; }
+            if (c != 0) { m0 = (int)(tm * TM); n0 = (int)(tn * TN); cls = c; return tl; }
         }
-        return tl < total ? tl : total;
     };
     int ahead = 0;        // stages issued and not yet consumed by this warp (warp 0 only)
     bool pdone = false;   // the end-of-sequence slot has been issued
@@ -406,7 +418,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_ws_kernel(const __grid_c
         if (++pkt == KT) {
             pkt = 0;
             ++ptseq;
-            ptile = seek(ptile + gridDim.x * GROUPS, pm0, pn0, pcls);
+            unsigned cur, end;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(cur), "=r"(end) : "r"(pst0 + 32) : "memory");
+            ptile = seek(cur, end, pm0, pn0, pcls);
+            if (lane == 0) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(pst0 + 32), "r"(cur), "r"(end) : "memory");
         }
         if (lane == 0) {
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pst0), "r"(ptile), "r"(pm0), "r"(pn0), "r"(pcls) : "memory");
@@ -425,12 +440,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_ws_kernel(const __grid_c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async;" ::: "memory");
     }
-    if (cw == 0 && lane == 0) {
-        int m0 = 0, n0 = 0, cls = 0;
-        const unsigned tl = seek(blockIdx.x * GROUPS + group, m0, n0, cls);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pst0), "r"(tl), "r"(m0), "r"(n0), "r"(cls) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pst0 + 16), "r"(0), "r"(0), "r"(0), "r"(0) : "memory");
-    }
     __syncthreads();
     long long pt0 = 0;
     if (PROF) pt0 = clock64();
@@ -440,6 +449,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_ws_kernel(const __grid_c
         for (unsigned waited = 0; waited < p.staggerNs; waited += 500u) __nanosleep(500u);
     }
     if (cw == 0) {
+        // the group's first tile (after the stagger: a late group simply draws later tiles), then fill the ring
+        int m0 = 0, n0 = 0, cls = 0;
+        unsigned cur = 0, end = 0;
+        const unsigned tl = seek(cur, end, m0, n0, cls);
+        if (lane == 0) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pst0), "r"(tl), "r"(m0), "r"(n0), "r"(cls) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pst0 + 16), "r"(0), "r"(0), "r"(0), "r"(0) : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(pst0 + 32), "r"(cur), "r"(end) : "memory");
+        }
+        __syncwarp();
 #pragma unroll 1
         for (int i = 0; i < STAGES && !pdone; ++i) produce(false);  // the ring starts empty: fill it
     }
@@ -601,8 +620,22 @@ bool make_map3(CUtensorMap* map, const double* ptr, i64 rows, i64 k, i64 ld, int
 
 int g_last_3d = 0;  // bit 0: A used the 3-D map, bit 1: B did (elb200_dgemm_ws_last_maps)
 
+// one zeroed tile counter per launch, from a ring long enough that a counter is never reused while an earlier
+// launch that used it can still be running (launches on different streams overlap at most a few deep)
+unsigned* next_tile_counter(cudaStream_t s) {
+    constexpr int RING = 4096;
+    static unsigned* ring = nullptr;
+    static unsigned long long used = 0;
+    if (!ring) ELB_CUDA(cudaMalloc((void**)&ring, RING * sizeof(unsigned)));
+    unsigned* c = ring + (used++ % RING);
+    ELB_CUDA(cudaMemsetAsync(c, 0, sizeof(unsigned), s));
+    return c;
+}
+
 template <bool AK, bool BKM, int MODE, bool PROF>
-void launch(const WsArgs& a, double flops, cudaStream_t s) {
+void launch(const WsArgs& a0, double flops, cudaStream_t s) {
+    WsArgs a = a0;
+    a.tileCounter = next_tile_counter(s);
     static bool configured = false;
     auto kern = gemm_f64_ws_kernel<AK, BKM, MODE, PROF>;
     if (!configured) {
