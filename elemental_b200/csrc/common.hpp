@@ -19,6 +19,7 @@ const char* last_error();
 // The stream every Fortran-ABI leaf (dgemm_, dtrsm_, ...) launches on.
 cudaStream_t current_stream();
 void set_current_stream(cudaStream_t s);
+void fortran_abi_fence();  // ELB200_BLAS_SYNC=1: the Fortran-ABI leaves synchronise before returning
 
 struct CudaError : std::runtime_error {
     explicit CudaError(const std::string& s) : std::runtime_error(s) {}

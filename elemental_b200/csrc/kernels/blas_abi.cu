@@ -9,6 +9,7 @@
 namespace {
 void report(int rc, const char* name) {
     if (rc != 0) fprintf(stderr, "elb200 %s: %s\n", name, elb200_last_error());
+    elb200::fortran_abi_fence();
 }
 elb200_stream_t cur() { return (elb200_stream_t)elb200::current_stream(); }
 }  // namespace

@@ -93,7 +93,7 @@ void lacpy_t(char uplo, i64 m, i64 n, const T* A, i64 lda, T* B, i64 ldb, cudaSt
     const int mode = u == 'U' ? 1 : (u == 'L' ? 2 : 0);
     if (mode == 0) {   // plain 2-D copy: the copy engine
         ELB_CUDA(cudaMemcpy2DAsync(B, sizeof(T) * (size_t)ldb, A, sizeof(T) * (size_t)lda, sizeof(T) * (size_t)m, (size_t)n,
-                                   cudaMemcpyDeviceToDevice, s));
+                                   cudaMemcpyDefault, s));   // Default: the arrays may be mapped host memory
         return;
     }
     dim3 grid((unsigned)ceil_div(m, 256), (unsigned)(n < 2048 ? n : 2048));
@@ -103,6 +103,7 @@ void lacpy_t(char uplo, i64 m, i64 n, const T* A, i64 lda, T* B, i64 ldb, cudaSt
 
 void report(int rc, const char* name) {
     if (rc != 0) fprintf(stderr, "elb200 %s: %s\n", name, elb200_last_error());
+    elb200::fortran_abi_fence();
 }
 cudaStream_t cur() { return current_stream(); }
 inline c32_t C32(elb200_c32 a) { return mk(a.re, a.im); }

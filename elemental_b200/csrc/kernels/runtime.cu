@@ -2,6 +2,7 @@
 // tensor-pipe (DMMA) ceiling probe that bench.py uses as roofline denominator.
 #include "../common.hpp"
 #include "elb200_blas.h"
+#include <cstdlib>
 #include <vector>
 
 namespace elb200 {
@@ -15,6 +16,18 @@ cudaStream_t current_stream() { return g_stream; }
 void set_current_stream(cudaStream_t s) { g_stream = s; }
 
 unsigned long long g_kernel_launches = 0;
+
+// ELB200_BLAS_SYNC=1: every Fortran-ABI entry point (dgemm_, dtrsm_, dscal_, ...) synchronises its stream before
+// returning, i.e. behaves like a host BLAS.  For callers that read the arrays from the host right after the call
+// without a fence of their own -- the unmodified reference linked against this library.
+void fortran_abi_fence() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = std::getenv("ELB200_BLAS_SYNC");
+        mode = (e && std::atoi(e) != 0) ? 1 : 0;
+    }
+    if (mode == 1) cudaStreamSynchronize(g_stream);
+}
 
 static int g_sm_limit = 0;
 int sm_limit() { return g_sm_limit; }

@@ -9,7 +9,51 @@ from pathlib import Path
 import numpy as np
 
 REF_LIB = Path(__file__).resolve().parent / "_ref" / "libElRef.so"
+# the same reference objects linked against libelb200.so's Fortran BLAS symbols with device-addressable buffers
+# (oracle/refbuild/Makefile target `dev`): the depth-1 integration of INTEGRATION.md, used by one GPU test
+REF_DEV_LIB = Path(__file__).resolve().parent / "_ref" / "libElRefDev.so"
 _lib = None
+
+
+_DEV = False
+_keep = []   # pinned staging buffers stay alive until the next call
+
+
+def use_device_build(on: bool = True):
+    """Switch every wrapper in this module between libElRef.so (CPU, the oracle) and libElRefDev.so.  The driver
+    ATTACHES the caller's arrays to DistMatrix objects, so in the device build they are staged through page-locked
+    (device-mapped) memory first -- a numpy array is pageable host memory the GPU cannot address."""
+    global _lib, REF_LIB, _DEV
+    _lib = None
+    _DEV = on
+    REF_LIB = (REF_DEV_LIB if on else Path(__file__).resolve().parent / "_ref" / "libElRef.so")
+
+
+def _pin(a):
+    """F-ordered copy of `a` in page-locked memory (torch's pinned allocator = cudaHostAlloc)."""
+    import torch
+    a = np.asarray(a)
+    tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+           np.dtype(np.complex64): torch.complex64, np.dtype(np.complex128): torch.complex128}[a.dtype]
+    t = torch.empty(tuple(reversed(a.shape)), dtype=tdt, pin_memory=True)
+    v = t.numpy().T          # Fortran-ordered view of the pinned block
+    v[...] = a
+    _keep.append(t)
+    return v
+
+
+class _InOut:
+    """the array the reference updates in place: the caller's array itself, or its pinned stand-in"""
+
+    def __init__(self, a):
+        self.user = a
+        self.buf = _pin(a) if _DEV else a
+
+    def done(self):
+        if _DEV:
+            self.user[...] = self.buf
+            del _keep[:]
+        return self.user
 
 
 class ReferenceUnavailable(RuntimeError):
@@ -52,7 +96,8 @@ def _p(a):
 
 
 def _f(a, dtype=None):
-    return np.asfortranarray(a, dtype=dtype)
+    a = np.asfortranarray(a, dtype=dtype)
+    return _pin(a) if _DEV else a
 
 
 def _scalar(x, dt):
@@ -83,25 +128,28 @@ def gemm(oa, ob, alpha, A, B, beta, Cm, nb=128, alg=0):
     ka, av = _scalar(alpha, dt)
     kb, bv = _scalar(beta, dt)
     fn = getattr(lib(), "elref_gemm_" + _SUF[dt])
+    io = _InOut(Cm)
     _chk(fn(C.c_char(oa.encode()), C.c_char(ob.encode()), m, n, k, av, _p(A), A.shape[0], _p(B), B.shape[0],
-            bv, _p(Cm), Cm.shape[0], int(nb), int(alg)))
-    return Cm
+            bv, _p(io.buf), Cm.shape[0], int(nb), int(alg)))
+    return io.done()
 
 
 def cholesky(uplo, A, nb=128):
     assert A.flags.f_contiguous
     fn = getattr(lib(), "elref_cholesky_" + _SUF[A.dtype])
-    _chk(fn(C.c_char(uplo.encode()), A.shape[0], _p(A), A.shape[0], int(nb)))
-    return A
+    io = _InOut(A)
+    _chk(fn(C.c_char(uplo.encode()), A.shape[0], _p(io.buf), A.shape[0], int(nb)))
+    return io.done()
 
 
 def hpd_solve(uplo, orient, A, B, nb=128):
     assert B.flags.f_contiguous
     A = _f(A, B.dtype)
     fn = getattr(lib(), "elref_hpdsolve_" + _SUF[B.dtype])
+    io = _InOut(B)
     _chk(fn(C.c_char(uplo.encode()), C.c_char(orient.encode()), A.shape[0], B.shape[1], _p(A), A.shape[0],
-            _p(B), B.shape[0], int(nb)))
-    return B
+            _p(io.buf), B.shape[0], int(nb)))
+    return io.done()
 
 
 def trsm(side, uplo, orient, diag, alpha, A, B, nb=128):
@@ -109,9 +157,10 @@ def trsm(side, uplo, orient, diag, alpha, A, B, nb=128):
     A = _f(A, B.dtype)
     ka, av = _scalar(alpha, B.dtype)
     fn = getattr(lib(), "elref_trsm_" + _SUF[B.dtype])
+    io = _InOut(B)
     _chk(fn(C.c_char(side.encode()), C.c_char(uplo.encode()), C.c_char(orient.encode()), C.c_char(diag.encode()),
-            B.shape[0], B.shape[1], av, _p(A), A.shape[0], _p(B), B.shape[0], int(nb)))
-    return B
+            B.shape[0], B.shape[1], av, _p(A), A.shape[0], _p(io.buf), B.shape[0], int(nb)))
+    return io.done()
 
 
 def herk(uplo, orient, alpha, A, beta, Cm, nb=128):
