@@ -403,6 +403,35 @@ def GemmHost(orientA, orientB, alpha, grid: Grid, m, n, k, A, B, beta, Cm, alg=G
               _scalar(dt, beta), pc, ldc, alg), "ElGemmDistHost")
 
 
+BINARY, BINARY_FLAT = 3, 4   # include/El/core/types.hpp:494-510
+
+
+def ReadBinaryFlat(A: DistMatrix, height, width, filename):
+    """El::read::BinaryFlat(A, height, width, filename) (src/io/Read/BinaryFlat.hpp:37-102) into device memory."""
+    _sync_stream()
+    _check(A._fn("ElReadBinaryFlatDist")(A._h, int(height), int(width), str(filename).encode()), "ElReadBinaryFlatDist")
+    return A
+
+
+def ReadBinary(A: DistMatrix, filename):
+    """El::read::Binary(A, filename) (src/io/Read/Binary.hpp): two Int header words, then the entries."""
+    _sync_stream()
+    _check(A._fn("ElReadBinaryDist")(A._h, str(filename).encode()), "ElReadBinaryDist")
+    return A
+
+
+def Write(A: DistMatrix, basename, fmt=BINARY):
+    """El::Write(A, basename, format) for BINARY (basename.bin) and BINARY_FLAT (basename.dat) (src/io/Write.cpp:46-63)."""
+    _sync_stream()
+    _check(A._fn("ElWriteDist")(A._h, str(basename).encode(), int(fmt)), "ElWriteDist")
+
+
+def AxpyTrapezoid(uplo, alpha, X: DistMatrix, Y: DistMatrix, offset=0):
+    """El::AxpyTrapezoid(uplo, alpha, X, Y, offset) (include/El/blas_like/level1/AxpyTrapezoid.hpp:128-160)."""
+    _sync_stream()
+    _check(_same(X, Y)._fn("ElAxpyTrapezoidDist")(uplo, _scalar(X.dtype, alpha), X._h, Y._h, int(offset)), "ElAxpyTrapezoidDist")
+
+
 def Syrk(uplo, orient, alpha, A: DistMatrix, beta, Cm: DistMatrix):
     _sync_stream()
     dt = _same(A, Cm).dtype

@@ -5,6 +5,7 @@
 
 #include "dev.hpp"
 #include "elb200/factor.hpp"
+#include "elb200/io.hpp"
 #include "elb200_El.h"
 
 using namespace El;
@@ -168,6 +169,23 @@ ElError ElRedistStats(uint64_t out[8], bool reset) {
     ElError ElZeroDist_##SUF(ElDistMatrix_##SUF A) { return Try([&] { Zero(*M_##SUF(A)); }); }                     \
     ElError ElScaleTrapezoidDist_##SUF(SCALAR alpha, ElUpperOrLower uplo, ElDistMatrix_##SUF A, ElInt offset) {    \
         return Try([&] { ScaleTrapezoid(Sc<T, SCALAR>(alpha), UL(uplo), *M_##SUF(A), offset); });                  \
+    }                                                                                                              \
+    ElError ElReadBinaryFlatDist_##SUF(ElDistMatrix_##SUF A, ElInt height, ElInt width, const char* filename) {    \
+        return Try([&] { read::BinaryFlat(*M_##SUF(A), height, width, filename); });                               \
+    }                                                                                                              \
+    ElError ElReadBinaryDist_##SUF(ElDistMatrix_##SUF A, const char* filename) {                                   \
+        return Try([&] { read::Binary(*M_##SUF(A), filename); });                                                  \
+    }                                                                                                              \
+    ElError ElWriteDist_##SUF(ElConstDistMatrix_##SUF A, const char* basename, int format) {                       \
+        return Try([&] {                                                                                           \
+            if (format == BINARY) write::Binary(*CM_##SUF(A), basename);                                           \
+            else if (format == BINARY_FLAT) write::BinaryFlat(*CM_##SUF(A), basename);                             \
+            else LogicError("Only the BINARY and BINARY_FLAT file formats are on this path");                      \
+        });                                                                                                        \
+    }                                                                                                              \
+    ElError ElAxpyTrapezoidDist_##SUF(ElUpperOrLower uplo, SCALAR alpha, ElConstDistMatrix_##SUF X,                \
+                                      ElDistMatrix_##SUF Y, ElInt offset) {                                        \
+        return Try([&] { AxpyTrapezoid(UL(uplo), Sc<T, SCALAR>(alpha), *CM_##SUF(X), *M_##SUF(Y), offset); });     \
     }                                                                                                              \
     ElError ElMakeTrapezoidalDist_##SUF(ElUpperOrLower uplo, ElDistMatrix_##SUF A, ElInt offset) {                 \
         return Try([&] { MakeTrapezoidal(UL(uplo), *M_##SUF(A), offset); });                                       \

@@ -392,10 +392,76 @@ void Syrk(UpperOrLower uplo, Orientation o, T alpha, const Matrix<T>& A, T beta,
     if (o == NORMAL) Trrk(uplo, NORMAL, other, alpha, A, A, beta, C);
     else Trrk(uplo, other, NORMAL, alpha, A, A, beta, C);
 }
+namespace {
+// Syrk with a long summation index (k > 10 n: syrk::LN_Dot / LT_Dot / UN_Dot / UT_Dot, Syrk/LN.hpp:88-128 and
+// siblings): distribute the summation index over all p processes once, then per block of C's triangle one local
+// product of the process's k / p slice and one sum-scatter.  Diagonal blocks are masked products into a zeroed
+// block, so the strictly-other triangle of C only ever receives zeros.  The block edge is GemmDotBlocksize (the
+// reference hard-codes 2000, a CPU-cache size).
+template <typename T>
+void SyrkDot(UpperOrLower uplo, Orientation o, T alpha, const AbstractDistMatrix<T>& A, AbstractDistMatrix<T>& C,
+             bool conjugate) {
+    const Grid& g = C.Grid();
+    const Int n = C.Height();
+    const Int blockSize = GemmDotBlocksize(sizeof(T));
+    const Orientation other = conjugate ? ADJOINT : TRANSPOSE;
+    const bool normal = (o == NORMAL);
+    AbstractDistMatrix<T> AV(g, normal ? STAR : VC, normal ? VC : STAR);
+    Copy(A, AV);
+    const Int k = normal ? AV.Width() : AV.Height();
+    AbstractDistMatrix<T> Z(g, STAR, STAR);
+    auto rows = [&](Int i0, Int h) {   // op(AV)(i0 : i0 + h, :) as a view of AV
+        return normal ? LockedView(static_cast<const AbstractDistMatrix<T>&>(AV), i0, 0, h, k)
+                      : LockedView(static_cast<const AbstractDistMatrix<T>&>(AV), 0, i0, k, h);
+    };
+    for (Int i0 = 0; i0 < n; i0 += blockSize) {
+        const Int bi = std::min(blockSize, n - i0);
+        auto Ai = rows(i0, bi);
+        // diagonal block
+        Zeros(Z, bi, bi);
+        if (normal) Trrk(uplo, NORMAL, other, alpha, Ai.LockedMatrix(), Ai.LockedMatrix(), T(0), Z.Matrix());
+        else Trrk(uplo, other, NORMAL, alpha, Ai.LockedMatrix(), Ai.LockedMatrix(), T(0), Z.Matrix());
+        {
+            auto Cii = View(C, i0, i0, bi, bi);
+            AxpyContract(T(1), static_cast<const AbstractDistMatrix<T>&>(Z), Cii);
+        }
+        // the blocks of this block row (UPPER) / block column (LOWER) beyond the diagonal
+        for (Int j0 = i0 + bi; j0 < n; j0 += blockSize) {
+            const Int bj = std::min(blockSize, n - j0);
+            auto Aj = rows(j0, bj);
+            if (uplo == LOWER) {   // C(J, I) += alpha op(A)_J op(A)_I'
+                Z.Resize(bj, bi);
+                if (normal) LocalGemm(NORMAL, other, alpha, Aj, Ai, T(0), Z);
+                else LocalGemm(other, NORMAL, alpha, Aj, Ai, T(0), Z);
+                auto Cji = View(C, j0, i0, bj, bi);
+                AxpyContract(T(1), static_cast<const AbstractDistMatrix<T>&>(Z), Cji);
+            } else {               // C(I, J) += alpha op(A)_I op(A)_J'
+                Z.Resize(bi, bj);
+                if (normal) LocalGemm(NORMAL, other, alpha, Ai, Aj, T(0), Z);
+                else LocalGemm(other, NORMAL, alpha, Ai, Aj, T(0), Z);
+                auto Cij = View(C, i0, j0, bi, bj);
+                AxpyContract(T(1), static_cast<const AbstractDistMatrix<T>&>(Z), Cij);
+            }
+        }
+    }
+}
+}  // namespace
+
 template <typename T>
 void Syrk(UpperOrLower uplo, Orientation o, T alpha, const AbstractDistMatrix<T>& A, T beta, AbstractDistMatrix<T>& C,
           bool conjugate) {
     const Orientation other = conjugate ? ADJOINT : TRANSPOSE;
+    const Int n = C.Height();
+    const Int k = (o == NORMAL) ? A.Width() : A.Height();
+    const double weightAwayFromDot = 10.;   // Syrk/LN.hpp:152-157
+    if (C.Width() == n && ((o == NORMAL) ? A.Height() : A.Width()) == n && k > weightAwayFromDot * n && n > 0) {
+        AssertSameGrid(A, C);
+        ReadWriteProxy<T> CP(C);
+        ScaleTrapezoid(beta, uplo, CP.Get());
+        SyrkDot(uplo, o, alpha, A, CP.Get(), conjugate);
+        CP.Commit();
+        return;
+    }
     if (o == NORMAL) Trrk(uplo, NORMAL, other, alpha, A, A, beta, C);
     else Trrk(uplo, other, NORMAL, alpha, A, A, beta, C);
 }

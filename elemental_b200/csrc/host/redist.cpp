@@ -423,6 +423,32 @@ void ScaleTrapezoid(T alpha, UpperOrLower uplo, AbstractDistMatrix<T>& A, Int of
                                         offset, (elb200_stream_t)dev::stream()),
                  "elb200_scale_trapezoid");
 }
+// Y_trap += alpha X_trap.  Equal distributions and alignments: LocalAxpyTrapezoid (AxpyTrapezoid.hpp:73-125), one
+// kernel on the local staircases; otherwise X is first brought into Y's distribution (:128-160).
+template <typename T>
+void LocalAxpyTrapezoid(UpperOrLower uplo, T alpha, const AbstractDistMatrix<T>& X, AbstractDistMatrix<T>& Y, Int offset) {
+    if (X.Height() != Y.Height() || X.Width() != Y.Width()) LogicError("Nonconformal AxpyTrapezoid");
+    if (X.ColDist() != Y.ColDist() || X.RowDist() != Y.RowDist() || X.ColAlign() != Y.ColAlign() ||
+        X.RowAlign() != Y.RowAlign())
+        LogicError("LocalAxpyTrapezoid needs identically distributed and aligned operands");
+    dev::D<T> a = dev::val<T>(alpha);
+    dev::c_check(elb200_axpy_trapezoid(dev::Code<T>(), &a, UpperOrLowerToChar(uplo), Y.LocalHeight(), Y.LocalWidth(),
+                                       X.LockedBuffer(), X.LDim(), Y.Buffer(), Y.LDim(), Y.ColShift(), Y.ColStride(),
+                                       Y.RowShift(), Y.RowStride(), offset, (elb200_stream_t)dev::stream()),
+                 "elb200_axpy_trapezoid");
+}
+template <typename T>
+void AxpyTrapezoid(UpperOrLower uplo, T alpha, const AbstractDistMatrix<T>& X, AbstractDistMatrix<T>& Y, Int offset) {
+    if (X.ColDist() == Y.ColDist() && X.RowDist() == Y.RowDist() && X.ColAlign() == Y.ColAlign() &&
+        X.RowAlign() == Y.RowAlign()) {
+        LocalAxpyTrapezoid(uplo, alpha, X, Y, offset);
+        return;
+    }
+    AbstractDistMatrix<T> XCopy(Y.Grid(), Y.ColDist(), Y.RowDist());
+    XCopy.AlignWith(Y);
+    Copy(X, XCopy);
+    LocalAxpyTrapezoid(uplo, alpha, static_cast<const AbstractDistMatrix<T>&>(XCopy), Y, offset);
+}
 template <typename T>
 void MakeTrapezoidal(UpperOrLower uplo, AbstractDistMatrix<T>& A, Int offset) {
     dev::c_check(elb200_make_trapezoidal(dev::Code<T>(), UpperOrLowerToChar(uplo), A.LocalHeight(), A.LocalWidth(),
@@ -517,6 +543,8 @@ Base<T> MaxNorm(const AbstractDistMatrix<T>& A) {
     template void Conjugate(AbstractDistMatrix<T>&);                                                  \
     template void ScaleTrapezoid(T, UpperOrLower, AbstractDistMatrix<T>&, Int);                       \
     template void MakeTrapezoidal(UpperOrLower, AbstractDistMatrix<T>&, Int);                         \
+    template void AxpyTrapezoid(UpperOrLower, T, const AbstractDistMatrix<T>&, AbstractDistMatrix<T>&, Int);      \
+    template void LocalAxpyTrapezoid(UpperOrLower, T, const AbstractDistMatrix<T>&, AbstractDistMatrix<T>&, Int); \
     template void HashFill(AbstractDistMatrix<T>&, int, uint64_t, double);                            \
     template Base<T> FrobeniusNorm(const AbstractDistMatrix<T>&);                                     \
     template Base<T> MaxNorm(const AbstractDistMatrix<T>&);

@@ -109,6 +109,32 @@ __global__ void __launch_bounds__(256) trapezoid_kernel(T alpha, int lower, i64 
     }
 }
 
+// Y += alpha X inside the trapezoid (same predicate), X and Y local matrices of identically distributed operands
+template <class T>
+__global__ void __launch_bounds__(256) axpy_trapezoid_kernel(T alpha, int lower, i64 m, i64 n, const T* __restrict__ X,
+                                                             i64 ldx, T* Y, i64 ldy, i64 gi0, i64 gis, i64 gj0, i64 gjs,
+                                                             i64 offset) {
+    const i64 i = (i64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= m) return;
+    const i64 gi = gi0 + i * gis;
+    for (i64 j = blockIdx.y; j < n; j += gridDim.y) {
+        const i64 gj = gj0 + j * gjs;
+        const bool inside = lower ? (gj - gi <= offset) : (gj - gi >= offset);
+        if (inside) Y[i + j * ldy] = Y[i + j * ldy] + alpha * X[i + j * ldx];
+    }
+}
+template <class T>
+void axpy_trapezoid_t(const void* alpha, char uplo, i64 m, i64 n, const void* X, i64 ldx, void* Y, i64 ldy, i64 gi0,
+                      i64 gis, i64 gj0, i64 gjs, i64 offset, cudaStream_t s) {
+    if (m <= 0 || n <= 0) return;
+    const char u = up(uplo);
+    if (u != 'L' && u != 'U') throw std::logic_error("axpy_trapezoid: uplo must be 'L' or 'U'");
+    T a = alpha ? *(const T*)alpha : scalar_traits<T>::from_real(1);
+    dim3 grid((unsigned)ceil_div(m, 256), (unsigned)(n < 1024 ? n : 1024));
+    axpy_trapezoid_kernel<T><<<grid, 256, 0, s>>>(a, u == 'L', m, n, (const T*)X, ldx, (T*)Y, ldy, gi0, gis, gj0, gjs, offset);
+    ELB_LAUNCH_CHECK();
+}
+
 template <class T, int MODE>
 void trapezoid_t(const void* alpha, char uplo, i64 m, i64 n, void* A, i64 lda, i64 gi0, i64 gis,
                  i64 gj0, i64 gjs, i64 offset, cudaStream_t s) {
@@ -309,6 +335,15 @@ int elb200_scale_trapezoid(int dtype, const void* alpha, char uplo, int64_t m, i
     return guarded([&] {
         DISPATCH_DTYPE(dtype, (trapezoid_t<T, 0>(alpha, uplo, m, n, A, lda, rowShift, rowStride, colShift,
                                                  colStride, offset, (cudaStream_t)s)));
+    });
+}
+
+int elb200_axpy_trapezoid(int dtype, const void* alpha, char uplo, int64_t m, int64_t n, const void* X, int64_t ldx,
+                          void* Y, int64_t ldy, int64_t rowShift, int64_t rowStride, int64_t colShift, int64_t colStride,
+                          int64_t offset, elb200_stream_t s) {
+    return guarded([&] {
+        DISPATCH_DTYPE(dtype, (axpy_trapezoid_t<T>(alpha, uplo, m, n, X, ldx, Y, ldy, rowShift, rowStride, colShift,
+                                                   colStride, offset, (cudaStream_t)s)));
     });
 }
 

@@ -5,3 +5,4 @@
 #include "elb200/core.hpp"
 #include "elb200/level3.hpp"
 #include "elb200/factor.hpp"
+#include "elb200/io.hpp"

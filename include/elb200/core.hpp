@@ -389,6 +389,9 @@ template <typename T> void Zeros(AbstractDistMatrix<T>& A, Int m, Int n);
 template <typename T> void Conjugate(AbstractDistMatrix<T>& A);
 template <typename T> void ScaleTrapezoid(T alpha, UpperOrLower uplo, AbstractDistMatrix<T>& A, Int offset = 0);
 template <typename T> void MakeTrapezoidal(UpperOrLower uplo, AbstractDistMatrix<T>& A, Int offset = 0);
+// Y_trap += alpha X_trap (include/El/blas_like/level1/AxpyTrapezoid.hpp:14-49,73-160)
+template <typename T> void AxpyTrapezoid(UpperOrLower uplo, T alpha, const AbstractDistMatrix<T>& X, AbstractDistMatrix<T>& Y, Int offset = 0);
+template <typename T> void LocalAxpyTrapezoid(UpperOrLower uplo, T alpha, const AbstractDistMatrix<T>& X, AbstractDistMatrix<T>& Y, Int offset = 0);
 template <typename T> void Copy(const Matrix<T>& A, Matrix<T>& B);
 // grid-independent counter-hash fill on global indices (kind 0 general, 1 Hermitian + diag)
 template <typename T> void HashFill(AbstractDistMatrix<T>& A, int kind, uint64_t seed, double diag = 0.0);

@@ -127,6 +127,14 @@ ElError ElRedistStats(uint64_t out[8], bool reset);
     ElError ElScaleDist_##SUF(SCALAR alpha, ElDistMatrix_##SUF A);                                          \
     ElError ElZeroDist_##SUF(ElDistMatrix_##SUF A);                                                         \
     ElError ElScaleTrapezoidDist_##SUF(SCALAR alpha, ElUpperOrLower uplo, ElDistMatrix_##SUF A, ElInt offset); \
+    /* BINARY (3) / BINARY_FLAT (4) matrix files of the reference (include/El/io.h: ElReadDist, ElWriteDist;   */ \
+    /* src/io/Read/{Binary,BinaryFlat}.hpp, Write/{Binary,BinaryFlat}.hpp) into / from device-resident matrices */ \
+    ElError ElReadBinaryFlatDist_##SUF(ElDistMatrix_##SUF A, ElInt height, ElInt width, const char* filename); \
+    ElError ElReadBinaryDist_##SUF(ElDistMatrix_##SUF A, const char* filename);                             \
+    ElError ElWriteDist_##SUF(ElConstDistMatrix_##SUF A, const char* basename, int format);                 \
+    /* ElAxpyTrapezoidDist (include/El/blas_like/level1.h): Y_trap += alpha X_trap */                       \
+    ElError ElAxpyTrapezoidDist_##SUF(ElUpperOrLower uplo, SCALAR alpha, ElConstDistMatrix_##SUF X,         \
+                                      ElDistMatrix_##SUF Y, ElInt offset);                                  \
     ElError ElMakeTrapezoidalDist_##SUF(ElUpperOrLower uplo, ElDistMatrix_##SUF A, ElInt offset);           \
     ElError ElFrobeniusNormDist_##SUF(ElConstDistMatrix_##SUF A, REAL* norm);                               \
     ElError ElMaxNormDist_##SUF(ElConstDistMatrix_##SUF A, REAL* norm);                                     \

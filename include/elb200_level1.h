@@ -11,6 +11,7 @@
  *                            (level1/AxpyContract.hpp:300-303) and Scale
  *   elb200_scale_trapezoid<- ScaleTrapezoid (level1/ScaleTrapezoid.hpp:14-86)
  *   elb200_make_trapezoidal <- MakeTrapezoidal
+ *   elb200_axpy_trapezoid <- AxpyTrapezoid / LocalAxpyTrapezoid (level1/AxpyTrapezoid.hpp:14-49,73-125)
  *   elb200_fill_hash      <- test/bench input generation on global indices (grid independent;
  *                            stands in for Uniform / HermitianUniformSpectrum)
  *   elb200_sumsq / elb200_maxabs <- FrobeniusNorm / MaxNorm pieces used by the residual checks
@@ -52,6 +53,11 @@ int elb200_lattice_copy(int dtype, const elb200_lattice* descs, int ndesc, int c
 int elb200_scale_trapezoid(int dtype, const void* alpha, char uplo, int64_t m, int64_t n, void* A,
                            int64_t lda, int64_t rowShift, int64_t rowStride, int64_t colShift,
                            int64_t colStride, int64_t offset, elb200_stream_t s);
+/* Y += alpha X restricted to the same trapezoid: AxpyTrapezoid / LocalAxpyTrapezoid
+ * (include/El/blas_like/level1/AxpyTrapezoid.hpp:14-49,73-125); X, Y local matrices of equally distributed operands */
+int elb200_axpy_trapezoid(int dtype, const void* alpha, char uplo, int64_t m, int64_t n, const void* X, int64_t ldx,
+                          void* Y, int64_t ldy, int64_t rowShift, int64_t rowStride, int64_t colShift, int64_t colStride,
+                          int64_t offset, elb200_stream_t s);
 /* Zero everything OUTSIDE that trapezoid. */
 int elb200_make_trapezoidal(int dtype, char uplo, int64_t m, int64_t n, void* A, int64_t lda,
                             int64_t rowShift, int64_t rowStride, int64_t colShift,

@@ -90,6 +90,73 @@ def main():
         El.PopBlocksizeStack()
         if not np.array_equal(hC, dC.LocalToHost()):
             fails.append(f"gemmhost {oa}{ob}")
+    # 2c. Syrk with a long summation index (the Dot variants), AxpyTrapezoid across distributions, the Trsm algorithms
+    El.SetGemmDotBlocksize(32)
+    for uplo in "LU":
+        for o in "NC":
+            n, k = 70, 900
+            A = O.fill(0, *((n, k) if o == "N" else (k, n)), 3, dtype=np.complex128)
+            C0 = O.fill(0, n, n, 4, dtype=np.complex128)
+            dC = dm(C0)
+            El.Herk(0 if uplo == "L" else 1, ORI[o], 1.25, dm(A), 0.5, dC)
+            P = A @ A.conj().T if o == "N" else A.conj().T @ A
+            mask = O._tri_mask(n, n, uplo)
+            want = np.where(mask, 1.25 * P + 0.5 * C0, C0)
+            got = dC.ToGlobal()
+            if not (np.array_equal(got[~mask], C0[~mask]) and
+                    np.linalg.norm(got - want) <= 4 * k * np.finfo(np.float64).eps * (np.linalg.norm(A) ** 2 + np.linalg.norm(C0))):
+                fails.append(f"herk dot {uplo}{o}")
+    El.SetGemmDotBlocksize(0)
+    X, Y0 = O.fill(0, 61, 61, 1), O.fill(0, 61, 61, 2)
+    ii, jj = np.indices((61, 61))
+    for uplo in "LU":
+        for xdist in ((0, 2), (3, 5), (5, 5), (2, 0)):
+            dY = dm(Y0, align=(r - 1, c - 1))
+            El.AxpyTrapezoid(0 if uplo == "L" else 1, 0.5, dm(X, xdist), dY, 1)
+            inside = (jj - ii <= 1) if uplo == "L" else (jj - ii >= 1)
+            if not np.array_equal(dY.ToGlobal(), np.where(inside, Y0 + 0.5 * X, Y0)):
+                fails.append(f"axpytrapezoid {uplo} {xdist}")
+    m, nbt = 150, 32
+    T = np.asfortranarray(O.fill(0, m, m, 9, dtype=np.complex128) / m + 2 * np.eye(m))
+    for nrhs in (40, 3, 1):
+        B0 = O.fill(0, m, nrhs, 10, dtype=np.complex128)
+        for uplo in "LU":
+            for tr in "NTC":
+                ref = (R.trsm("L", uplo, tr, "N", 2.0, T, B0.copy(order="F"), nb=nbt) if R.available()
+                       else O.trsm("L", uplo, tr, "N", 2.0, T, B0.copy(order="F"), nb=nbt))
+                for alg in (0, 1, 2, 3):
+                    dB = dm(B0)
+                    El.PushBlocksizeStack(nbt)
+                    El.Trsm(0, 0 if uplo == "L" else 1, ORI[tr], 0, 2.0, dm(T), dB, False, alg)
+                    El.PopBlocksizeStack()
+                    if not np.linalg.norm(dB.ToGlobal() - ref) <= 50 * m * np.finfo(np.float64).eps * np.linalg.norm(ref):
+                        fails.append(f"trsm alg={alg} {uplo}{tr} nrhs={nrhs}")
+    # 2d. BINARY / BINARY_FLAT files written and read by all ranks (columns through [*,VC])
+    import tempfile
+    tdir = os.environ.get("ELB200_TEST_TMP", tempfile.gettempdir())
+    base = os.path.join(tdir, f"elb200_mgpu_io_{world}_{os.environ.get('MASTER_PORT', '0')}")
+    Gio = O.fill(0, 93, 57, 21, dtype=np.complex128)
+    dG = dm(Gio, align=(r - 1, 0))
+    El.Write(dG, base, El.BINARY)
+    El.Write(dG, base, El.BINARY_FLAT)
+    dist.barrier()
+    raw = np.asfortranarray(Gio).tobytes(order="F")
+    if open(base + ".dat", "rb").read() != raw or open(base + ".bin", "rb").read() != np.array([93, 57], dtype=np.int32).tobytes() + raw:
+        fails.append("binary file bytes")
+    for dd in ((0, 2), (5, 3), (3, 5), (2, 0)):
+        Bio = El.DistMatrix(np.complex128, dd[0], dd[1], g)
+        El.ReadBinary(Bio, base + ".bin")
+        Bf = El.DistMatrix(np.complex128, dd[0], dd[1], g)
+        El.ReadBinaryFlat(Bf, 93, 57, base + ".dat")
+        if not (np.array_equal(Bio.ToGlobal(), Gio) and np.array_equal(Bf.ToGlobal(), Gio)):
+            fails.append(f"binary read {dd}")
+    dist.barrier()
+    if rank == 0:
+        for ext in (".bin", ".dat"):
+            try:
+                os.remove(base + ext)
+            except OSError:
+                pass
     # 3. Cholesky / HPDSolve / Trsm
     for dt in (np.float64, np.complex128):
         n, nb = 300, 64

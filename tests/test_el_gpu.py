@@ -329,6 +329,56 @@ def test_syrk_herk_trrk_dist_with_beta(El, dt):
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.complex128])
+def test_syrk_dot_variant_long_summation_index(El, dt):
+    """k > 10 n selects syrk::{LN,LT,UN,UT}_Dot (Syrk/LN.hpp:88-157): summation index over all processes, one local
+    product and one sum-scatter per block of the triangle.  Small Dot blocksize so that several blocks are formed."""
+    n, k = 70, 900
+    e = np.finfo(np.float64).eps
+    El.SetGemmDotBlocksize(32)
+    try:
+        for uplo in "LU":
+            for o in "NTC":
+                conj = o == "C"
+                A = O.fill(0, *((n, k) if o == "N" else (k, n)), 3, dtype=dt)
+                C0 = O.fill(0, n, n, 4, dtype=dt)
+                dC = _dm(El, C0)
+                if conj:
+                    El.Herk(UL[uplo], ORI[o], 1.25, _dm(El, A), 0.5, dC)
+                    P = A.conj().T @ A
+                elif o == "T":
+                    El.Syrk(UL[uplo], ORI[o], 1.25, _dm(El, A), 0.5, dC)
+                    P = A.T @ A
+                else:
+                    El.Syrk(UL[uplo], ORI[o], 1.25, _dm(El, A), 0.5, dC)
+                    P = A @ A.T
+                mask = O._tri_mask(n, n, uplo)
+                want = np.where(mask, 1.25 * P + 0.5 * C0, C0)
+                got = dC.ToGlobal()
+                assert np.array_equal(got[~mask], C0[~mask]), (dt, uplo, o)
+                assert np.linalg.norm(got - want) <= 4 * k * e * (np.linalg.norm(A) ** 2 + np.linalg.norm(C0)), (dt, uplo, o)
+    finally:
+        El.SetGemmDotBlocksize(0)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex64])
+def test_axpy_trapezoid_dist(El, dt):
+    """AxpyTrapezoid (level1/AxpyTrapezoid.hpp:128-160): same distribution -> local staircase kernel; different
+    distribution -> X is redistributed first.  Bit-exact for alpha a power of two."""
+    n = 61
+    X, Y0 = O.fill(0, n, n, 1, dtype=dt), O.fill(0, n, n, 2, dtype=dt)
+    ii, jj = np.indices((n, n))
+    for uplo in "LU":
+        for off in (0, 2, -3):
+            inside = (jj - ii <= off) if uplo == "L" else (jj - ii >= off)
+            want = np.where(inside, Y0 + dt(0.5) * X, Y0)
+            for xdist in ((El.MC, El.MR), (El.VC, El.STAR), (El.STAR, El.STAR)):
+                dX = El.DistMatrix(dt, xdist[0], xdist[1]); dX.FromGlobal(X)
+                dY = _dm(El, Y0)
+                El.AxpyTrapezoid(UL[uplo], 0.5, dX, dY, off)
+                assert np.array_equal(dY.ToGlobal(), want), (uplo, off, xdist)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128])
 def test_herk_trrk_dist(El, dt):
     n, k, nb = 170, 90, 48
     for uplo in "LU":
@@ -373,3 +423,27 @@ def test_views_and_blocksize_stack(El):
     El.PushBlocksizeStack(77); assert El.Blocksize() == 77
     El.SetBlocksize(55); assert El.Blocksize() == 55
     El.PopBlocksizeStack(); assert El.Blocksize() == b0
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128, np.float32])
+def test_binary_and_binaryflat_files_device_roundtrip(El, dt, tmp_path):
+    """BINARY / BINARY_FLAT (src/io/Write/Binary.hpp:16-36, Write/BinaryFlat.hpp:16-33, Read/Binary.hpp,
+    Read/BinaryFlat.hpp:37-102): the bytes on disk are the reference's -- column-major entries, BINARY prefixed by two
+    32-bit Ints -- and files in that layout read back bit-exactly into any distribution."""
+    h, w = 93, 57
+    A = O.fill(0, h, w, 21, dtype=dt)
+    dA = _dm(El, A)
+    El.Write(dA, str(tmp_path / "m"), El.BINARY)
+    El.Write(dA, str(tmp_path / "m"), El.BINARY_FLAT)
+    raw = np.asfortranarray(A).tobytes(order="F")
+    assert (tmp_path / "m.dat").read_bytes() == raw
+    assert (tmp_path / "m.bin").read_bytes() == np.array([h, w], dtype=np.int32).tobytes() + raw
+    for dist in ((El.MC, El.MR), (El.STAR, El.VC), (El.VC, El.STAR), (El.STAR, El.STAR), (El.MR, El.MC)):
+        B = El.DistMatrix(dt, dist[0], dist[1])
+        El.ReadBinaryFlat(B, h, w, str(tmp_path / "m.dat"))
+        assert np.array_equal(B.ToGlobal(), A), dist
+        B2 = El.DistMatrix(dt, dist[0], dist[1])
+        El.ReadBinary(B2, str(tmp_path / "m.bin"))
+        assert (B2.Height(), B2.Width()) == (h, w) and np.array_equal(B2.ToGlobal(), A), dist
+    with pytest.raises(El.Elb200Error):
+        El.ReadBinaryFlat(El.DistMatrix(dt), h + 1, w, str(tmp_path / "m.dat"))   # size check (BinaryFlat.hpp:24-28)
