@@ -213,6 +213,12 @@ int tcode(char c, const char* what) {
 }
 }  // namespace
 
+bool zgemm_real_device(int mode, int ta, int tb, i64 m, i64 n, i64 k, c64_t alpha, const c64_t* A, i64 lda,
+                       const c64_t* B, i64 ldb, c64_t beta, c64_t* C, i64 ldc, i64 gi0, i64 gis, i64 gj0, i64 gjs,
+                       bool realDiag, cudaStream_t s);
+int g_zgemm_path = 0;   // 0 automatic, 1 always the complex cp.async kernel (elb200_zgemm_set_path)
+int g_zgemm_last = 0;   // 1 complex kernel, 2 real persistent kernel
+
 void zgemm_device_ex(int mode, char transA, char transB, i64 m, i64 n, i64 k, c64_t alpha, const c64_t* A, i64 lda,
                      const c64_t* B, i64 ldb, c64_t beta, c64_t* C, i64 ldc, i64 gi0, i64 gis, i64 gj0, i64 gjs,
                      bool realDiag, cudaStream_t s) {
@@ -222,6 +228,13 @@ void zgemm_device_ex(int mode, char transA, char transB, i64 m, i64 n, i64 k, c6
     if (lda < ((ta ? k : m) > 1 ? (ta ? k : m) : 1)) throw std::logic_error("zgemm: lda too small");
     if (ldb < ((tb ? n : k) > 1 ? (tb ? n : k) : 1)) throw std::logic_error("zgemm: ldb too small");
     if (ldc < (m > 1 ? m : 1)) throw std::logic_error("zgemm: ldc too small");
+    // large products run on the real persistent kernel (gemm_c64_real.cu): same flops, tensor pipe at the real rate
+    if (g_zgemm_path != 1 &&
+        zgemm_real_device(mode, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, gi0, gis, gj0, gjs, realDiag, s)) {
+        g_zgemm_last = 2;
+        return;
+    }
+    g_zgemm_last = 1;
     ZArgs a;
     a.m = m; a.n = n; a.k = (alpha.re == 0.0 && alpha.im == 0.0) ? 0 : k;
     a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc;
@@ -242,3 +255,10 @@ void zgemm_device(int mode, char ta, char tb, i64 m, i64 n, i64 k, c64_t alpha, 
 }
 
 }  // namespace elb200
+
+extern "C" {
+// 0 automatic (large products on the real persistent kernel), 1 always the dedicated complex kernel
+void elb200_zgemm_set_path(int p) { elb200::g_zgemm_path = p; }
+// which kernel the last zgemm / ztrrk / zherk / zsyrk call used: 1 complex cp.async kernel, 2 real persistent kernel
+int elb200_zgemm_last_kernel(void) { return elb200::g_zgemm_last; }
+}

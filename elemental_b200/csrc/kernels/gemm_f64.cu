@@ -28,7 +28,7 @@ extern int g_dgemm_last_kernel;
 // gemm_f64_ws.cu: persistent TMA-fed kernel; false when the operands are not TMA-eligible
 bool dgemm_ws_device(int mode, bool ta, bool tb, i64 m, i64 n, i64 k, double alpha, const double* A, i64 lda,
                      const double* B, i64 ldb, double beta, double* C, i64 ldc, i64 gi0, i64 gis, i64 gj0, i64 gjs,
-                     double flops, cudaStream_t s);
+                     double flops, cudaStream_t s, int rowPair = 0);
 namespace {
 
 constexpr int BK = 16;

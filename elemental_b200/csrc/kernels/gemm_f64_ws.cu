@@ -85,6 +85,7 @@ struct WsArgs {
     int alphaMode;    // 0: general, 1: alpha == 1, 2: alpha == -1
     int bandw;        // tile columns per rasterisation band
     unsigned staggerNs;  // group 1 starts this much later than group 0
+    int rowPair;      // 1: rows 2i, 2i + 1 of C are (re, im) of complex row i: the staircase mask uses row >> 1
     unsigned* tileCounter;  // zeroed before the launch: tiles are handed out in raster order, TILE_CHUNK at a time
 };
 
@@ -189,12 +190,14 @@ __device__ __forceinline__ int tile_class(const WsArgs& p, i64 m0, i64 n0) {
     if (MODE == 0) return full ? 2 : 1;
     const i64 mlast = (m0 + TM - 1 < p.m - 1) ? (m0 + TM - 1) : (p.m - 1);
     const i64 nlast = (n0 + TN - 1 < p.n - 1) ? (n0 + TN - 1) : (p.n - 1);
+    const int rp = p.rowPair;   // complex rows stored as (re, im) row pairs
+    const i64 rfirst = m0 >> rp, rlast = mlast >> rp, rend = (m0 + TM - 1) >> rp;
     if (MODE == 1) {
-        if (!(p.gi0 + mlast * p.gis >= p.gj0 + n0 * p.gjs)) return 0;                 // no gi >= gj
-        return (full && p.gi0 + m0 * p.gis >= p.gj0 + (n0 + TN - 1) * p.gjs) ? 2 : 1;  // all gi >= gj
+        if (!(p.gi0 + rlast * p.gis >= p.gj0 + n0 * p.gjs)) return 0;                     // no gi >= gj
+        return (full && p.gi0 + rfirst * p.gis >= p.gj0 + (n0 + TN - 1) * p.gjs) ? 2 : 1;  // all gi >= gj
     }
-    if (!(p.gi0 + m0 * p.gis <= p.gj0 + nlast * p.gjs)) return 0;
-    return (full && p.gi0 + (m0 + TM - 1) * p.gis <= p.gj0 + n0 * p.gjs) ? 2 : 1;
+    if (!(p.gi0 + rfirst * p.gis <= p.gj0 + nlast * p.gjs)) return 0;
+    return (full && p.gi0 + rend * p.gis <= p.gj0 + n0 * p.gjs) ? 2 : 1;
 }
 
 // ---- epilogue of one finished group tile (all 8 warps of the group) ----
@@ -289,8 +292,8 @@ __device__ __forceinline__ void epilogue(const WsArgs& p, double (&acc)[FM][FN][
                 for (int i = 0; i < FM; ++i) {
                     const i64 row = m0 + wm0 + tile_row<A_KMAJOR>(i, g);
                     bool v = (col < p.n) && (row < p.m);
-                    if (MODE == 1) v = v && (p.gi0 + row * p.gis >= gj);
-                    if (MODE == 2) v = v && (p.gi0 + row * p.gis <= gj);
+                    if (MODE == 1) v = v && (p.gi0 + (row >> p.rowPair) * p.gis >= gj);
+                    if (MODE == 2) v = v && (p.gi0 + (row >> p.rowPair) * p.gis <= gj);
                     ok[e][i] = v;
                     old[e][i] = (v && epi == 2) ? __ldcg(cptr + row) : 0.0;
                 }
@@ -669,7 +672,7 @@ void dispatch(bool ak, bool bk, const WsArgs& a, double flops, cudaStream_t s) {
 // ta / tb: op(A) / op(B) is the transpose of the stored matrix.
 bool dgemm_ws_device(int mode, bool ta, bool tb, i64 m, i64 n, i64 k, double alpha, const double* A, i64 lda,
                      const double* B, i64 ldb, double beta, double* C, i64 ldc, i64 gi0, i64 gis, i64 gj0, i64 gjs,
-                     double flops, cudaStream_t s) {
+                     double flops, cudaStream_t s, int rowPair) {
     if (k <= 0 || m <= 0 || n <= 0) return false;
     if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda & 1) || (ldb & 1)) return false;
     if (m >= (i64(1) << 31) - TM || n >= (i64(1) << 31) - TN || k >= (i64(1) << 31) - BK) return false;
@@ -706,6 +709,7 @@ bool dgemm_ws_device(int mode, bool ta, bool tb, i64 m, i64 n, i64 k, double alp
     a.C = C; a.ldc = ldc;
     a.alpha = alpha; a.beta = beta;
     a.gi0 = gi0; a.gis = gis; a.gj0 = gj0; a.gjs = gjs;
+    a.rowPair = rowPair ? 1 : 0;
     a.tilesM = ceil_div(m, TM);
     a.tilesN = ceil_div(n, TN);
     a.prof = g_dgemm_ws_prof;

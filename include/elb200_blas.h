@@ -92,6 +92,11 @@ int elb200_cgemm(char transA, char transB, int64_t m, int64_t n, int64_t k,
                  elb200_c32 alpha, const elb200_c32* A, int64_t lda,
                  const elb200_c32* B, int64_t ldb,
                  elb200_c32 beta, elb200_c32* C, int64_t ldc, elb200_stream_t s);
+/* Complex<double> products: 0 = automatic (large ones run on the real persistent kernel through the
+ * (re, im)-row-pair identity of kernels/gemm_c64_real.cu), 1 = always the dedicated complex kernel.
+ * elb200_zgemm_last_kernel: 1 complex cp.async kernel, 2 real persistent kernel. */
+void elb200_zgemm_set_path(int path);
+int elb200_zgemm_last_kernel(void);
 /* float GEMM on tcgen05 (kind::tf32) with the 3xTF32 operand split;
  * relative error per product ~2^-21 instead of 2^-24 */
 /* the 3xTF32 kernel's tile rasterisation (host copy of the device function; tests check it is a bijection) */
