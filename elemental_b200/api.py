@@ -492,6 +492,14 @@ def Trmm(side, uplo, orient, diag, alpha, A: DistMatrix, B: DistMatrix):
 TRSM_DEFAULT, TRSM_LARGE, TRSM_MEDIUM, TRSM_SMALL = 0, 1, 2, 3
 
 
+def Trr2k(uplo, orientA, orientB, orientC, orientD, alpha, A, B, beta, Cm, D, gamma, E):
+    """El::Trr2k (src/blas_like/level3/Trr2k.cpp:34-...): E_tri := alpha op(A) op(B) + beta op(C) op(D) + gamma E_tri."""
+    _sync_stream()
+    dt = _same(A, B, Cm, D, E).dtype
+    _check(E._fn("ElTrr2kDist")(uplo, orientA, orientB, orientC, orientD, _scalar(dt, alpha), A._h, B._h,
+                                _scalar(dt, beta), Cm._h, D._h, _scalar(dt, gamma), E._h), "ElTrr2kDist")
+
+
 def Trsm(side, uplo, orient, diag, alpha, A: DistMatrix, B: DistMatrix, checkIfSingular=False, alg=TRSM_DEFAULT):
     """El::Trsm(side, uplo, orientation, diag, alpha, A, B, checkIfSingular, alg) (src/blas_like/level3/Trsm.cpp:67-375);
     raises SingularMatrixException when checkIfSingular finds a zero diagonal entry."""

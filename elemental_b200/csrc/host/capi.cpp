@@ -264,6 +264,15 @@ ElError ElRedistStats(uint64_t out[8], bool reset) {
                   *M_##SUF(C), false);                                                                             \
         });                                                                                                        \
     }                                                                                                              \
+    ElError ElTrr2kDist_##SUF(ElUpperOrLower uplo, ElOrientation oA, ElOrientation oB, ElOrientation oC,           \
+                              ElOrientation oD, SCALAR alpha, ElConstDistMatrix_##SUF A, ElConstDistMatrix_##SUF B, \
+                              SCALAR beta, ElConstDistMatrix_##SUF C, ElConstDistMatrix_##SUF D, SCALAR gamma,     \
+                              ElDistMatrix_##SUF E) {                                                              \
+        return Try([&] {                                                                                           \
+            Trr2k(UL(uplo), O(oA), O(oB), O(oC), O(oD), Sc<T, SCALAR>(alpha), *CM_##SUF(A), *CM_##SUF(B),          \
+                  Sc<T, SCALAR>(beta), *CM_##SUF(C), *CM_##SUF(D), Sc<T, SCALAR>(gamma), *M_##SUF(E));             \
+        });                                                                                                        \
+    }                                                                                                              \
     ElError ElTrmmDist_##SUF(ElLeftOrRight side, ElUpperOrLower uplo, ElOrientation o, ElUnitOrNonUnit diag,       \
                              SCALAR alpha, ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B) {                      \
         return Try([&] {                                                                                           \

@@ -279,6 +279,78 @@ void SummaDot(Orientation oA, Orientation oB, T alpha, const AbstractDistMatrix<
     }
 }
 
+// Cannon's algorithm on a square grid (Gemm/NN.hpp:15-89): every process keeps one package of A and one of B;
+// after an initial skew the package of A moves one process to the left and the package of B one process up per
+// step, and the local product of what a process holds is accumulated into its block of C.  sqrt(p) steps, each
+// moving the WHOLE local matrices once -- the least data of any variant.  The ring shifts are ncclSend / ncclRecv
+// pairs inside the row and the column communicator; packages are double-buffered, so the shift for step q + 1 runs
+// on the panel stream underneath the product of step q.
+template <typename T>
+void CannonNN(T alpha, const AbstractDistMatrix<T>& APre, const AbstractDistMatrix<T>& BPre, AbstractDistMatrix<T>& C) {
+    const Grid& g = C.Grid();
+    if (g.Height() != g.Width()) LogicError("Process grid must be square for Cannon's");
+    const int ps = g.Height();
+    if (APre.Width() % ps != 0) LogicError("For now, width(A) must be integer multiple of sqrt(p)");
+    // A and B in [MC,MR], A's rows aligned with C's, B's columns aligned with C's (NN.hpp:29-36)
+    AbstractDistMatrix<T> Ac(g, MC, MR), Bc(g, MC, MR);
+    const AbstractDistMatrix<T>* A = &APre;
+    const AbstractDistMatrix<T>* B = &BPre;
+    if (APre.ColAlign() != C.ColAlign()) { Ac.AlignCols(C.ColAlign()); Copy(APre, Ac); A = &Ac; }
+    if (BPre.RowAlign() != C.RowAlign()) { Bc.AlignRows(C.RowAlign()); Copy(BPre, Bc); B = &Bc; }
+    const int row = g.Row(), col = g.Col();
+    const Int lhA = A->LocalHeight(), lwA = A->LocalWidth(), lhB = B->LocalHeight(), lwB = B->LocalWidth();
+    Matrix<T> pkgA[2] = {Matrix<T>(lhA, lwA), Matrix<T>(lhA, lwA)};
+    Matrix<T> pkgB[2] = {Matrix<T>(lhB, lwB), Matrix<T>(lhB, lwB)};
+    Copy(A->LockedMatrix(), pkgA[0]);
+    Copy(B->LockedMatrix(), pkgB[0]);
+    cudaStream_t mainS = dev::stream();
+    auto shift = [&](Matrix<T>& from, Matrix<T>& to, const Comm& comm, int sendTo, int recvFrom, cudaStream_t s) {
+        // packages of one ring all have the same local shape (width(A) is a multiple of sqrt(p); the other
+        // dimension is shared by the whole grid row / column)
+        const size_t bytes = sizeof(T) * size_t(from.LDim()) * size_t(from.Width());
+        if (comm.size == 1 || (sendTo == comm.rank && recvFrom == comm.rank)) {
+            ELB_CUDA(cudaMemcpyAsync(to.Buffer(), from.LockedBuffer(), bytes, cudaMemcpyDeviceToDevice, s));
+            return;
+        }
+        ELB_NCCL(ncclGroupStart());
+        ELB_NCCL(ncclSend(from.LockedBuffer(), bytes, ncclInt8, sendTo, (ncclComm_t)comm.nccl, s));
+        ELB_NCCL(ncclRecv(to.Buffer(), bytes, ncclInt8, recvFrom, (ncclComm_t)comm.nccl, s));
+        ELB_NCCL(ncclGroupEnd());
+    };
+    auto mod = [&](int x) { return ((x % ps) + ps) % ps; };
+    // initial skew (NN.hpp:55-64): afterwards the column residue of A's package equals the row residue of B's
+    const int rowShiftA = A->RowShift(), colShiftB = B->ColShift();
+    int cur = 0;
+    if (ps > 1) {
+        shift(pkgA[0], pkgA[1], g.MRComm(), mod(col - colShiftB), mod(col + colShiftB), mainS);
+        shift(pkgB[0], pkgB[1], g.MCComm(), mod(row - rowShiftA), mod(row + rowShiftA), mainS);
+        cur = 1;
+    }
+    const bool overlap = ps > 1 && dev::OverlapEnabled();
+    cudaStream_t panelS = overlap ? elb200::aux_stream(0) : mainS;
+    dev::Event ready, consumed[2], fork;
+    for (int q = 0; q < ps; ++q) {
+        const int nxt = cur ^ 1;
+        if (q != ps - 1) {
+            // the packages of step q are final on the main stream; the next ones may be overwritten once the product
+            // that last read them (step q - 1) is done
+            fork.Record(mainS);
+            fork.Wait(panelS);
+            if (q >= 1) consumed[nxt].Wait(panelS);
+            shift(pkgA[cur], pkgA[nxt], g.MRComm(), mod(col - 1), mod(col + 1), panelS);
+            shift(pkgB[cur], pkgB[nxt], g.MCComm(), mod(row - 1), mod(row + 1), panelS);
+            ready.Record(panelS);
+        }
+        {
+            dev::SmLimitScope lim(q != ps - 1 && overlap ? std::max(1, elb200::sm_count() - dev::PanelSms(8)) : 0);
+            LocalGemmRaw('N', 'N', alpha, pkgA[cur], pkgB[cur], T(1), C.Matrix());
+        }
+        consumed[cur].Record(mainS);
+        if (q != ps - 1) ready.Wait(mainS);
+        cur = nxt;
+    }
+}
+
 }  // namespace
 
 template <typename T>
@@ -305,6 +377,10 @@ void Gemm(Orientation oA, Orientation oB, T alpha, const AbstractDistMatrix<T>& 
         case GEMM_SUMMA_B: SummaB(oA, oB, alpha, A, B, C); break;
         case GEMM_SUMMA_C: SummaC(oA, oB, alpha, A, B, C); break;
         case GEMM_SUMMA_DOT: SummaDot(oA, oB, alpha, A, B, C); break;
+        case GEMM_CANNON:   // only the NN case has it (Gemm/NN.hpp:283, NT/TN/TT reject it)
+            if (oA != NORMAL || oB != NORMAL) LogicError("Unsupported Gemm option");
+            CannonNN(alpha, A, B, C);
+            break;
         default: LogicError("Unsupported Gemm option");
     }
     CP.Commit();
@@ -485,9 +561,86 @@ template <> Complex<float> ConjIf(Complex<float> a, bool c) { return c ? std::co
 template <> Complex<double> ConjIf(Complex<double> a, bool c) { return c ? std::conj(a) : a; }
 }  // namespace
 
+// ---- Trr2k: E_tri := alpha op(A) op(B) + beta op(C) op(D) + gamma E_tri ----
+// The reference's LocalTrr2k (src/blas_like/level3/Trr2k/Local.hpp, 276 lines) recurses like LocalTrrk with two
+// products per leaf.  Here the two products are ONE masked tensor-pipe GEMM: with L = [alpha op(A) | beta op(C)]
+// and R = [op(B) ; op(D)] stacked along the summation index, L R = alpha op(A) op(B) + beta op(C) op(D), so E's
+// triangle is read and written once per panel step instead of twice.  The stacking is two strided device copies of
+// panel-sized data (alpha / beta, transposition and conjugation folded in).
+template <typename T>
+void LocalTrr2k(UpperOrLower uplo, Orientation oA, Orientation oB, Orientation oC, Orientation oD, T alpha,
+                const AbstractDistMatrix<T>& A, const AbstractDistMatrix<T>& B, T beta, const AbstractDistMatrix<T>& C,
+                const AbstractDistMatrix<T>& D, T gamma, AbstractDistMatrix<T>& E) {
+    const Matrix<T>&Al = A.LockedMatrix(), &Bl = B.LockedMatrix(), &Cl = C.LockedMatrix(), &Dl = D.LockedMatrix();
+    Matrix<T>& El_ = E.Matrix();
+    const Int m = El_.Height(), n = El_.Width();
+    const Int kA = (oA == NORMAL) ? Al.Width() : Al.Height(), kC = (oC == NORMAL) ? Cl.Width() : Cl.Height();
+    auto rowsOf = [](Orientation o, const Matrix<T>& M) { return o == NORMAL ? M.Height() : M.Width(); };
+    auto colsOf = [](Orientation o, const Matrix<T>& M) { return o == NORMAL ? M.Width() : M.Height(); };
+    if (rowsOf(oA, Al) != m || rowsOf(oC, Cl) != m || colsOf(oB, Bl) != n || colsOf(oD, Dl) != n ||
+        rowsOf(oB, Bl) != kA || rowsOf(oD, Dl) != kC)
+        LogicError("Nonconformal LocalTrr2k");
+    ScaleTrapezoid(gamma, uplo, E);
+    if (m == 0 || n == 0 || kA + kC == 0) return;
+    const Int kk = kA + kC;
+    Matrix<T> Lm(m, kk), Rm(kk, n);
+    typedef dev::D<T> DT;
+    auto place = [&](Orientation o, const Matrix<T>& src, Matrix<T>& dst, Int i0, Int j0, Int h, Int w, const T* scale) {
+        // dst(i0 : i0 + h, j0 : j0 + w) = scale * op(src)
+        if (h == 0 || w == 0) return;
+        DT sc = dev::val<T>(scale ? *scale : T(1));
+        const bool tr = (o != NORMAL);
+        elb200::lattice_copy_device<DT>(dev::ptr(src.LockedBuffer()), dev::ptr(dst.Buffer()), h, w, 0, tr ? src.LDim() : 1,
+                                        tr ? 1 : src.LDim(), i0 + (elb200::i64)j0 * dst.LDim(), 1, dst.LDim(),
+                                        o == ADJOINT, scale ? &sc : nullptr, false, dev::stream());
+    };
+    place(oA, Al, Lm, 0, 0, m, kA, alpha == T(1) ? nullptr : &alpha);
+    place(oC, Cl, Lm, 0, kA, m, kC, beta == T(1) ? nullptr : &beta);
+    place(oB, Bl, Rm, 0, 0, kA, n, nullptr);
+    place(oD, Dl, Rm, kA, 0, kC, n, nullptr);
+    elb200::gemm_device<DT>(uplo == LOWER ? 1 : 2, 'N', 'N', m, n, kk, dev::val<T>(T(1)), dev::ptr(Lm.LockedBuffer()),
+                            Lm.LDim(), dev::ptr(Rm.LockedBuffer()), Rm.LDim(), dev::val<T>(T(1)), dev::ptr(El_.Buffer()),
+                            El_.LDim(), E.ColShift(), E.ColStride(), E.RowShift(), E.RowStride(), dev::stream());
+}
+
+// Trr2k.cpp:34-...: panel loop at Blocksize(); every orientation case reduces to "form the four panels in
+// [MC,*] / [*,MR], one LocalTrr2k".
+template <typename T>
+void Trr2k(UpperOrLower uplo, Orientation oA, Orientation oB, Orientation oC, Orientation oD, T alpha,
+           const AbstractDistMatrix<T>& APre, const AbstractDistMatrix<T>& BPre, T beta,
+           const AbstractDistMatrix<T>& CPre, const AbstractDistMatrix<T>& DPre, T gamma, AbstractDistMatrix<T>& EPre) {
+    AssertSameGrid(APre, EPre); AssertSameGrid(BPre, EPre); AssertSameGrid(CPre, EPre); AssertSameGrid(DPre, EPre);
+    const Int n = EPre.Height();
+    const Int k = (oA == NORMAL) ? APre.Width() : APre.Height();
+    auto dimsOk = [&](Orientation o, const AbstractDistMatrix<T>& M, bool left) {
+        const Int r = (o == NORMAL) ? M.Height() : M.Width(), c = (o == NORMAL) ? M.Width() : M.Height();
+        return left ? (r == n && c == k) : (r == k && c == n);
+    };
+    if (EPre.Width() != n || !dimsOk(oA, APre, true) || !dimsOk(oC, CPre, true) || !dimsOk(oB, BPre, false) ||
+        !dimsOk(oD, DPre, false))
+        LogicError("Nonconformal Trr2k");
+    ReadProxy<T> AP(APre), BP(BPre), CP(CPre), DP(DPre);
+    ReadWriteProxy<T> EP(EPre);
+    const auto &A = AP.Get(), &B = BP.Get(), &C = CP.Get(), &D = DP.Get();
+    auto& E = EP.Get();
+    const Grid& g = E.Grid();
+    ScaleTrapezoid(gamma, uplo, E);
+    const Int bsize = Blocksize();
+    AbstractDistMatrix<T> A1(g, MC, STAR), C1(g, MC, STAR), B1(g, STAR, MR), D1(g, STAR, MR);
+    A1.AlignWith(E); C1.AlignWith(E); B1.AlignWith(E); D1.AlignWith(E);
+    for (Int s = 0; s < k; s += bsize) {
+        const Int nb = std::min(bsize, k - s);
+        FormPanel(oA, A, 0, s, n, nb, A1);
+        FormPanel(oC, C, 0, s, n, nb, C1);
+        FormPanel(oB, B, s, 0, nb, n, B1);
+        FormPanel(oD, D, s, 0, nb, n, D1);
+        LocalTrr2k(uplo, NORMAL, NORMAL, NORMAL, NORMAL, alpha, A1, B1, beta, C1, D1, T(1), E);
+    }
+    EP.Commit();
+}
+
 // C_tri := alpha op(A) op(B)' + alphaSec op(B) op(A)' + beta C_tri, alphaSec = conj(alpha) for Her2k
-// (Syr2k/LN.hpp:25).  The reference fuses both products in LocalTrr2k; two masked rank-k updates do
-// the same arithmetic with one more pass over the triangle of C.
+// (Syr2k/LN.hpp:14-63 and siblings): one Trr2k, i.e. one pass over the triangle of C per panel step.
 template <typename T>
 void Syr2k(UpperOrLower uplo, Orientation o, T alpha, const AbstractDistMatrix<T>& A, const AbstractDistMatrix<T>& B,
            T beta, AbstractDistMatrix<T>& C, bool conjugate) {
@@ -498,13 +651,8 @@ void Syr2k(UpperOrLower uplo, Orientation o, T alpha, const AbstractDistMatrix<T
         LogicError("Nonconformal Syr2k");
     const Orientation other = conjugate ? ADJOINT : TRANSPOSE;
     const T alphaSec = ConjIf(alpha, conjugate);
-    if (normal) {
-        Trrk(uplo, NORMAL, other, alpha, A, B, beta, C);
-        Trrk(uplo, NORMAL, other, alphaSec, B, A, T(1), C);
-    } else {
-        Trrk(uplo, other, NORMAL, alpha, A, B, beta, C);
-        Trrk(uplo, other, NORMAL, alphaSec, B, A, T(1), C);
-    }
+    if (normal) Trr2k(uplo, NORMAL, other, NORMAL, other, alpha, A, B, alphaSec, B, A, beta, C);
+    else Trr2k(uplo, other, NORMAL, other, NORMAL, alpha, A, B, alphaSec, B, A, beta, C);
 }
 template <typename T>
 void Her2k(UpperOrLower uplo, Orientation o, T alpha, const AbstractDistMatrix<T>& A, const AbstractDistMatrix<T>& B,
@@ -911,6 +1059,12 @@ void Trsm(LeftOrRight side, UpperOrLower uplo, Orientation o, UnitOrNonUnit diag
                        AbstractDistMatrix<T>&);                                                                      \
     template void Syr2k(UpperOrLower, Orientation, T, const AbstractDistMatrix<T>&, const AbstractDistMatrix<T>&, T, \
                         AbstractDistMatrix<T>&, bool);                                                               \
+    template void Trr2k(UpperOrLower, Orientation, Orientation, Orientation, Orientation, T,                        \
+                        const AbstractDistMatrix<T>&, const AbstractDistMatrix<T>&, T, const AbstractDistMatrix<T>&, \
+                        const AbstractDistMatrix<T>&, T, AbstractDistMatrix<T>&);                                    \
+    template void LocalTrr2k(UpperOrLower, Orientation, Orientation, Orientation, Orientation, T,                   \
+                             const AbstractDistMatrix<T>&, const AbstractDistMatrix<T>&, T,                          \
+                             const AbstractDistMatrix<T>&, const AbstractDistMatrix<T>&, T, AbstractDistMatrix<T>&); \
     template void Her2k(UpperOrLower, Orientation, T, const AbstractDistMatrix<T>&, const AbstractDistMatrix<T>&,    \
                         Base<T>, AbstractDistMatrix<T>&);                                                            \
     template void Symm(LeftOrRight, UpperOrLower, T, const AbstractDistMatrix<T>&, const AbstractDistMatrix<T>&, T,  \

@@ -417,6 +417,7 @@ void Conjugate(AbstractDistMatrix<T>& A) {
 }
 template <typename T>
 void ScaleTrapezoid(T alpha, UpperOrLower uplo, AbstractDistMatrix<T>& A, Int offset) {
+    if (alpha == T(1)) return;
     dev::D<T> a = dev::val<T>(alpha);
     dev::c_check(elb200_scale_trapezoid(dev::Code<T>(), &a, UpperOrLowerToChar(uplo), A.LocalHeight(), A.LocalWidth(),
                                         A.Buffer(), A.LDim(), A.ColShift(), A.ColStride(), A.RowShift(), A.RowStride(),

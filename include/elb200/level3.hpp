@@ -73,11 +73,22 @@ void Herk(UpperOrLower uplo, Orientation orientation, Base<T> alpha, const Abstr
 
 // ---- Syr2k / Her2k, Symm / Hemm, Trmm (siblings over the same leaves) ----
 // Reference: src/blas_like/level3/Syr2k.cpp + Syr2k/{LN,LT,UN,UT}.hpp (LocalTrr2k), Symm.cpp + Symm/*.hpp,
-// Trmm.cpp + Trmm/*.hpp.  Here: Syr2k = two masked rank-k updates (Trrk); Symm = Gemm on the mirrored
+// Trmm.cpp + Trmm/*.hpp.  Here: Syr2k = Trr2k (one masked GEMM over the stacked panels per step); Symm = Gemm on the mirrored
 // triangle (an n x n temporary: sized for HBM, not for a CPU cache); Trmm = Gemm on the trapezoid copy.
 template <typename T>
 void Syr2k(UpperOrLower uplo, Orientation orientation, T alpha, const AbstractDistMatrix<T>& A,
            const AbstractDistMatrix<T>& B, T beta, AbstractDistMatrix<T>& C, bool conjugate = false);
+// E_tri := alpha op(A) op(B) + beta op(C) op(D) + gamma E_tri (src/blas_like/level3/Trr2k.cpp:34-...,
+// include/El/blas_like/level3.hpp:592-640); LocalTrr2k takes the panels already in [MC,*] / [*,MR] (or their
+// transposes) and runs ONE masked GEMM over the stacked summation index (Trr2k/Local.hpp does two products per leaf)
+template <typename T>
+void Trr2k(UpperOrLower uplo, Orientation orientA, Orientation orientB, Orientation orientC, Orientation orientD,
+           T alpha, const AbstractDistMatrix<T>& A, const AbstractDistMatrix<T>& B, T beta,
+           const AbstractDistMatrix<T>& C, const AbstractDistMatrix<T>& D, T gamma, AbstractDistMatrix<T>& E);
+template <typename T>
+void LocalTrr2k(UpperOrLower uplo, Orientation orientA, Orientation orientB, Orientation orientC,
+                Orientation orientD, T alpha, const AbstractDistMatrix<T>& A, const AbstractDistMatrix<T>& B, T beta,
+                const AbstractDistMatrix<T>& C, const AbstractDistMatrix<T>& D, T gamma, AbstractDistMatrix<T>& E);
 template <typename T>
 void Her2k(UpperOrLower uplo, Orientation orientation, T alpha, const AbstractDistMatrix<T>& A,
            const AbstractDistMatrix<T>& B, Base<T> beta, AbstractDistMatrix<T>& C);

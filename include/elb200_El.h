@@ -178,6 +178,12 @@ ElError ElRedistStats(uint64_t out[8], bool reset);
     ElError ElSyr2kDist_##SUF(ElUpperOrLower uplo, ElOrientation orientation, SCALAR alpha,                 \
                               ElConstDistMatrix_##SUF A, ElConstDistMatrix_##SUF B, SCALAR beta,            \
                               ElDistMatrix_##SUF C);                                                        \
+    /* ElTrr2kDist (include/El/blas_like/level3.h): E_tri := alpha op(A) op(B) + beta op(C) op(D) + gamma E_tri */ \
+    ElError ElTrr2kDist_##SUF(ElUpperOrLower uplo, ElOrientation orientA, ElOrientation orientB,            \
+                              ElOrientation orientC, ElOrientation orientD, SCALAR alpha,                   \
+                              ElConstDistMatrix_##SUF A, ElConstDistMatrix_##SUF B, SCALAR beta,            \
+                              ElConstDistMatrix_##SUF C, ElConstDistMatrix_##SUF D, SCALAR gamma,           \
+                              ElDistMatrix_##SUF E);                                                        \
     ElError ElTrmmDist_##SUF(ElLeftOrRight side, ElUpperOrLower uplo, ElOrientation orientation,            \
                              ElUnitOrNonUnit diag, SCALAR alpha, ElConstDistMatrix_##SUF A,                 \
                              ElDistMatrix_##SUF B);                                                         \

@@ -75,6 +75,17 @@ def main():
                     res = O.gemm_residual(dC.ToGlobal(), ref, k, A, B)
                     if not res <= 1.0:
                         fails.append(f"gemm {dt.__name__} {oa}{ob} alg={alg} res={res}")
+    # 2a. Cannon's algorithm on square grids (Gemm/NN.hpp:15-89), with and without matching alignments
+    if r == c:
+        for dt in (np.float64, np.complex128):
+            m, n, k = 150, 130, 64 * r
+            A, B, C0 = O.fill(0, m, k, 1, dtype=dt), O.fill(0, k, n, 2, dtype=dt), O.fill(0, m, n, 3, dtype=dt)
+            for al in (None, (r - 1, c - 1)):
+                dC = dm(C0)
+                El.Gemm(0, 0, 3.0, dm(A, align=al), dm(B, align=al), 4.0, dC, El.GEMM_CANNON)
+                res = O.gemm_residual(dC.ToGlobal(), 3.0 * A @ B + 4.0 * C0, k, A, B)
+                if not res <= 1.0:
+                    fails.append(f"cannon {dt.__name__} align={al} res={res}")
     # 2b. GemmHost: host-resident local matrices streamed in column bands, against the device Gemm (bit-identical
     #     for alpha = -1, SUMMA_C: the same rank-nb updates in the same order)
     for (oa, ob) in (("N", "N"), ("N", "T"), ("C", "N")):

@@ -86,6 +86,19 @@ def test_gemm_host_streamed_matches_device_gemm(El, dt):
                     assert O.gemm_residual(hC, want, k, A, B) <= 1.0, (dt, oa, ob, alpha, alg)
 
 
+def test_gemm_cannon_nn(El):
+    """GEMM_CANNON (Gemm/NN.hpp:15-89) on the square grid at hand (1x1 here; tests/mgpu_worker.py runs it on 2x2): the
+    ring-shift product must agree with the reference's result; the other orientations reject the option as the
+    reference does (NT.hpp / TN.hpp / TT.hpp: "Unsupported Gemm option")."""
+    m, n, k = 96, 80, 64
+    A, B, C0 = O.fill(0, m, k, 1), O.fill(0, k, n, 2), O.fill(0, m, n, 3)
+    dC = _dm(El, C0)
+    El.Gemm(El.NORMAL, El.NORMAL, 3.0, _dm(El, A), _dm(El, B), 4.0, dC, El.GEMM_CANNON)
+    assert O.gemm_residual(dC.ToGlobal(), 3.0 * A @ B + 4.0 * C0, k, A, B) <= 1.0
+    with pytest.raises(El.Elb200Error):
+        El.Gemm(El.TRANSPOSE, El.NORMAL, 1.0, _dm(El, np.asfortranarray(A.T)), _dm(El, B), 0.0, _dm(El, C0), El.GEMM_CANNON)
+
+
 def test_gemm_float_3xtf32_mode_summa_dot(El):
     """BASELINE.json configs[4] in miniature: El::Gemm float, tall-skinny k (auto-selects SUMMA_Dot, NN.hpp:305),
     exact-FFMA mode vs 3xTF32 mode, both against the FP64 product.  Tolerance (north_star):

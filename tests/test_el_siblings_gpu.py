@@ -102,3 +102,39 @@ def test_trmm(El, dt):
                     El.Trmm(LR[side], UL[uplo], ORI[orient], DG[diag], alpha, dA, dB)
                     El.PopBlocksizeStack()
                     assert np.linalg.norm(dB.ToGlobal() - ref) <= _tol(ka, dt, A, B0), (dt, side, uplo, orient, diag)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128])
+def test_trr2k_all_orientation_cases(El, dt):
+    """El::Trr2k (src/blas_like/level3/Trr2k.cpp:34-...): E_tri := alpha op(A) op(B) + beta op(C) op(D) + gamma E_tri
+    for the 16 NORMAL / (conjugate-)transposed cases; here one masked GEMM over the stacked panels per step.  The
+    strictly-other triangle of E must stay bit-identical."""
+    n, k, nb = 130, 70, 32
+    alpha = 0.7 if dt == np.float64 else 0.7 - 0.3j
+    beta = -1.25 if dt == np.float64 else -1.25 + 0.5j
+    gamma = 0.5
+    e = np.finfo(np.float64).eps
+    tr = "C" if dt == np.complex128 else "T"
+    op = lambda M, o: M if o == "N" else (M.T if o == "T" else M.conj().T)
+    for uplo in "LU":
+        for oa in ("N", tr):
+            for ob in ("N", tr):
+                for oc in ("N", tr):
+                    for od in ("N", tr):
+                        A = O.fill(0, *((n, k) if oa == "N" else (k, n)), 1, dtype=dt)
+                        B = O.fill(0, *((k, n) if ob == "N" else (n, k)), 2, dtype=dt)
+                        Cc = O.fill(0, *((n, k) if oc == "N" else (k, n)), 3, dtype=dt)
+                        D = O.fill(0, *((k, n) if od == "N" else (n, k)), 4, dtype=dt)
+                        E0 = O.fill(0, n, n, 5, dtype=dt)
+                        dE = _dm(El, E0)
+                        El.PushBlocksizeStack(nb)
+                        El.Trr2k(UL[uplo], ORI[oa], ORI[ob], ORI[oc], ORI[od], alpha, _dm(El, A), _dm(El, B), beta,
+                                 _dm(El, Cc), _dm(El, D), gamma, dE)
+                        El.PopBlocksizeStack()
+                        mask = O._tri_mask(n, n, uplo)
+                        full = alpha * (op(A, oa) @ op(B, ob)) + beta * (op(Cc, oc) @ op(D, od)) + gamma * E0
+                        want = np.where(mask, full, E0)
+                        got = dE.ToGlobal()
+                        assert np.array_equal(got[~mask], E0[~mask]), (dt, uplo, oa, ob, oc, od)
+                        bound = 8 * k * e * (np.linalg.norm(A) * np.linalg.norm(B) + np.linalg.norm(Cc) * np.linalg.norm(D) + np.linalg.norm(E0))
+                        assert np.linalg.norm(got - want) <= bound, (dt, uplo, oa, ob, oc, od)
