@@ -481,7 +481,43 @@ def main():
         torch.cuda.empty_cache()
         return out
 
+    # ---- the other paths of section 8 that had no performance line: stationary-A / -B SUMMA on a shape that selects
+    #      them by the reference's rule (Gemm/NN.hpp:304-313), and the UPPER factorisation ----
+    def run_more():
+        out = {}
+        El.SetBlocksize(nb)
+        kk = max(nb, n // 8)
+        for name, (mm, nn_) in (("summa_a", (n, kk)), ("summa_b", (kk, n))):
+            A = El.DistMatrix(np.float64, El.MC, El.MR, grid, mm, n).HashFill(0, 1)
+            B = El.DistMatrix(np.float64, El.MC, El.MR, grid, n, nn_).HashFill(0, 2)
+            Cx = El.DistMatrix(np.float64, El.MC, El.MR, grid, mm, nn_).HashFill(0, 3)
+            alg = El.GEMM_SUMMA_A if name == "summa_a" else El.GEMM_SUMMA_B
+            fn = lambda: El.Gemm(El.NORMAL, El.NORMAL, 1.0, A, B, 1.0, Cx, alg)
+            timed(fn, 1)
+            t = timed(fn, 1)
+            out[name] = {"workload": f"El::Gemm NN double m={mm} n={nn_} k={n} {name.upper()} nb={nb}", "ms": t,
+                         "value": 2.0 * mm * nn_ * n / (t * 1e-3) / 1e9, "unit": "GFLOP/s"}
+            del A, B, Cx
+            torch.cuda.empty_cache()
+        if not args.no_potrf:
+            pn, pnb = args.potrf_n, args.potrf_nb
+            El.SetBlocksize(pnb)
+            H = El.DistMatrix(np.float64, El.MC, El.MR, grid, pn, pn)
+            ts = []
+            for it in range(2):
+                H.HashFill(1, 5, float(pn))
+                t = timed(lambda: El.Cholesky(El.UPPER, H), 1)
+                if it > 0:
+                    ts.append(t)
+            out["dpotrf_upper"] = {"workload": f"El::Cholesky UPPER double HPD n={pn} nb={pnb}", "ms": ts[0],
+                                   "value": (pn ** 3 / 3.0) / (ts[0] * 1e-3) / 1e9, "unit": "GFLOP/s"}
+            del H
+            torch.cuda.empty_cache()
+            El.SetBlocksize(nb)
+        return out
+
     orient = _guard(run_orient, "dgemm_orientations") if not args.no_orient else None
+    more = _guard(run_more, "more") if not args.no_orient else None
     hpd = _guard(run_hpd, "zhpdsolve") if not args.no_hpdsolve else None
     sg = _guard(run_sg, "sgemm_dot") if not args.no_sgemm else None
 
@@ -515,6 +551,8 @@ def main():
         }
         if orient:
             line["dgemm_orientations"] = orient
+        if more:
+            line["other_paths"] = more
         if potrf:
             line["dpotrf"] = potrf
         if hpd:

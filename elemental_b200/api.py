@@ -492,6 +492,18 @@ def Trmm(side, uplo, orient, diag, alpha, A: DistMatrix, B: DistMatrix):
 TRSM_DEFAULT, TRSM_LARGE, TRSM_MEDIUM, TRSM_SMALL = 0, 1, 2, 3
 
 
+def TwoSidedTrsm(uplo, diag, A: DistMatrix, B: DistMatrix):
+    """El::TwoSidedTrsm (src/blas_like/level3/TwoSidedTrsm.cpp): A := inv(L) A inv(L)^H / inv(U)^H A inv(U)."""
+    _sync_stream()
+    _check(_same(A, B)._fn("ElTwoSidedTrsmDist")(uplo, diag, A._h, B._h), "ElTwoSidedTrsmDist")
+
+
+def TwoSidedTrmm(uplo, diag, A: DistMatrix, B: DistMatrix):
+    """El::TwoSidedTrmm (src/blas_like/level3/TwoSidedTrmm.cpp): A := L^H A L / U A U^H."""
+    _sync_stream()
+    _check(_same(A, B)._fn("ElTwoSidedTrmmDist")(uplo, diag, A._h, B._h), "ElTwoSidedTrmmDist")
+
+
 def Trr2k(uplo, orientA, orientB, orientC, orientD, alpha, A, B, beta, Cm, D, gamma, E):
     """El::Trr2k (src/blas_like/level3/Trr2k.cpp:34-...): E_tri := alpha op(A) op(B) + beta op(C) op(D) + gamma E_tri."""
     _sync_stream()
@@ -519,6 +531,18 @@ def Cholesky(uplo, A: DistMatrix):
     """El::Cholesky(uplo, A) (src/lapack_like/factor/Cholesky.cpp:95-110); raises NonHPDMatrixException."""
     _sync_stream()
     _check(A._fn("ElCholeskyDist")(uplo, A._h), "ElCholeskyDist")
+
+
+def ReverseCholesky(uplo, A: DistMatrix):
+    """El::ReverseCholesky(uplo, A) (src/lapack_like/factor/Cholesky.cpp:129-137): A = L^H L (LOWER) / U U^H (UPPER)."""
+    _sync_stream()
+    _check(A._fn("ElReverseCholeskyDist")(uplo, A._h), "ElReverseCholeskyDist")
+
+
+def CholeskyVariant2(uplo, A: DistMatrix):
+    """cholesky::LowerVariant2Blocked / UpperVariant2Blocked (Cholesky/LowerVariant2.hpp:43-110): left-looking."""
+    _sync_stream()
+    _check(A._fn("ElCholeskyVariant2Dist")(uplo, A._h), "ElCholeskyVariant2Dist")
 
 
 def CholeskySolveAfter(uplo, orient, A: DistMatrix, B: DistMatrix):

@@ -264,6 +264,14 @@ ElError ElRedistStats(uint64_t out[8], bool reset) {
                   *M_##SUF(C), false);                                                                             \
         });                                                                                                        \
     }                                                                                                              \
+    ElError ElTwoSidedTrsmDist_##SUF(ElUpperOrLower uplo, ElUnitOrNonUnit diag, ElDistMatrix_##SUF A,              \
+                                     ElConstDistMatrix_##SUF B) {                                                  \
+        return Try([&] { TwoSidedTrsm(UL(uplo), static_cast<UnitOrNonUnit>(diag), *M_##SUF(A), *CM_##SUF(B)); });  \
+    }                                                                                                              \
+    ElError ElTwoSidedTrmmDist_##SUF(ElUpperOrLower uplo, ElUnitOrNonUnit diag, ElDistMatrix_##SUF A,              \
+                                     ElConstDistMatrix_##SUF B) {                                                  \
+        return Try([&] { TwoSidedTrmm(UL(uplo), static_cast<UnitOrNonUnit>(diag), *M_##SUF(A), *CM_##SUF(B)); });  \
+    }                                                                                                              \
     ElError ElTrr2kDist_##SUF(ElUpperOrLower uplo, ElOrientation oA, ElOrientation oB, ElOrientation oC,           \
                               ElOrientation oD, SCALAR alpha, ElConstDistMatrix_##SUF A, ElConstDistMatrix_##SUF B, \
                               SCALAR beta, ElConstDistMatrix_##SUF C, ElConstDistMatrix_##SUF D, SCALAR gamma,     \
@@ -281,6 +289,15 @@ ElError ElRedistStats(uint64_t out[8], bool reset) {
         });                                                                                                        \
     }                                                                                                              \
     ElError ElCholeskyDist_##SUF(ElUpperOrLower uplo, ElDistMatrix_##SUF A) { return Try([&] { Cholesky(UL(uplo), *M_##SUF(A)); }); } \
+    ElError ElReverseCholeskyDist_##SUF(ElUpperOrLower uplo, ElDistMatrix_##SUF A) {                               \
+        return Try([&] { ReverseCholesky(UL(uplo), *M_##SUF(A)); });                                               \
+    }                                                                                                              \
+    ElError ElCholeskyVariant2Dist_##SUF(ElUpperOrLower uplo, ElDistMatrix_##SUF A) {                              \
+        return Try([&] {                                                                                           \
+            if (UL(uplo) == LOWER) cholesky::LowerVariant2Blocked(*M_##SUF(A));                                    \
+            else cholesky::UpperVariant2Blocked(*M_##SUF(A));                                                      \
+        });                                                                                                        \
+    }                                                                                                              \
     ElError ElCholeskySolveAfterDist_##SUF(ElUpperOrLower uplo, ElOrientation o, ElConstDistMatrix_##SUF A,        \
                                            ElDistMatrix_##SUF B) {                                                 \
         return Try([&] { cholesky::SolveAfter(UL(uplo), O(o), *CM_##SUF(A), *M_##SUF(B)); });                      \

@@ -714,6 +714,49 @@ void Trmm(LeftOrRight side, UpperOrLower uplo, Orientation o, UnitOrNonUnit diag
              beta, B, GEMM_DEFAULT);
 }
 
+// ---- TwoSidedTrsm / TwoSidedTrmm (src/blas_like/level3/TwoSidedTrsm.cpp, TwoSidedTrmm.cpp, */LVar4.hpp, */UVar4.hpp) ----
+//   TwoSidedTrsm: A := inv(L) A inv(L)^H (LOWER) / inv(U)^H A inv(U) (UPPER);  TwoSidedTrmm: A := L^H A L / U A U^H,
+// A Hermitian with only its `uplo` triangle stored and updated.  The reference's variant-4 loops exploit the
+// symmetry (n^3 flops) with eight distributed temporaries per step; here the Hermitian matrix is completed once
+// (one transposing redistribution, as Hemm does) and the two one-sided operations run on the tensor pipe through
+// the Trsm / Trmm of this file -- 2 n^3 flops, every one of them in a large GEMM -- and the `uplo` triangle of the
+// result is written back; the other triangle of A is left untouched, as in the reference.
+namespace {
+template <typename F>
+void TwoSided(bool solve, UpperOrLower uplo, UnitOrNonUnit diag, AbstractDistMatrix<F>& A, const AbstractDistMatrix<F>& B) {
+    AssertSameGrid(A, B);
+    const Int n = A.Height();
+    if (A.Width() != n || B.Height() != n || B.Width() != n) LogicError("Nonconformal two-sided triangular operation");
+    if (n == 0) return;
+    const Grid& g = A.Grid();
+    AbstractDistMatrix<F> H(g, MC, MR), Ht(g, MC, MR);
+    Copy(static_cast<const AbstractDistMatrix<F>&>(A), H);
+    MakeTrapezoidal(uplo, H, 0);
+    Ht.AlignWith(H);
+    Transpose(static_cast<const AbstractDistMatrix<F>&>(H), Ht, true);
+    MakeTrapezoidal(uplo == LOWER ? UPPER : LOWER, Ht, uplo == LOWER ? 1 : -1);
+    Axpy(F(1), static_cast<const AbstractDistMatrix<F>&>(Ht), H);
+    Ht.Empty();
+    if (solve) {
+        if (uplo == LOWER) { Trsm(LEFT, LOWER, NORMAL, diag, F(1), B, H); Trsm(RIGHT, LOWER, ADJOINT, diag, F(1), B, H); }
+        else { Trsm(LEFT, UPPER, ADJOINT, diag, F(1), B, H); Trsm(RIGHT, UPPER, NORMAL, diag, F(1), B, H); }
+    } else {
+        if (uplo == LOWER) { Trmm(LEFT, LOWER, ADJOINT, diag, F(1), B, H); Trmm(RIGHT, LOWER, NORMAL, diag, F(1), B, H); }
+        else { Trmm(LEFT, UPPER, NORMAL, diag, F(1), B, H); Trmm(RIGHT, UPPER, ADJOINT, diag, F(1), B, H); }
+    }
+    ScaleTrapezoid(F(0), uplo, A);
+    AxpyTrapezoid(uplo, F(1), static_cast<const AbstractDistMatrix<F>&>(H), A);
+}
+}  // namespace
+template <typename F>
+void TwoSidedTrsm(UpperOrLower uplo, UnitOrNonUnit diag, AbstractDistMatrix<F>& A, const AbstractDistMatrix<F>& B) {
+    TwoSided(true, uplo, diag, A, B);
+}
+template <typename F>
+void TwoSidedTrmm(UpperOrLower uplo, UnitOrNonUnit diag, AbstractDistMatrix<F>& A, const AbstractDistMatrix<F>& B) {
+    TwoSided(false, uplo, diag, A, B);
+}
+
 // ---------------------------------------------------------------------------
 // Trsm
 // ---------------------------------------------------------------------------
@@ -1076,6 +1119,8 @@ void Trsm(LeftOrRight side, UpperOrLower uplo, Orientation o, UnitOrNonUnit diag
     template void Trsm(LeftOrRight, UpperOrLower, Orientation, UnitOrNonUnit, T, const Matrix<T>&, Matrix<T>&, bool); \
     template void Trsm(LeftOrRight, UpperOrLower, Orientation, UnitOrNonUnit, T, const AbstractDistMatrix<T>&,       \
                        AbstractDistMatrix<T>&, bool, TrsmAlgorithm);                                                 \
+    template void TwoSidedTrsm(UpperOrLower, UnitOrNonUnit, AbstractDistMatrix<T>&, const AbstractDistMatrix<T>&);   \
+    template void TwoSidedTrmm(UpperOrLower, UnitOrNonUnit, AbstractDistMatrix<T>&, const AbstractDistMatrix<T>&);   \
     template void Trsv(UpperOrLower, Orientation, UnitOrNonUnit, const AbstractDistMatrix<T>&,                       \
                        AbstractDistMatrix<T>&);                                                                      \
     template void LocalTrsm(LeftOrRight, UpperOrLower, Orientation, UnitOrNonUnit, T, const AbstractDistMatrix<T>&,  \

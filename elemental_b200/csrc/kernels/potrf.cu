@@ -5,13 +5,16 @@
 // UpperVariant3.hpp:16-46: sqrt + Scal + Her per column, i.e. level-2 BLAS run
 // redundantly on every rank) with ONE single-CTA kernel that keeps the working
 // panel in shared memory:
-//   for each 32-column block:   warp 0 factors the 32x32 diagonal block in
-//   registers (shuffles, no memory traffic), every thread then solves one row
-//   of the panel below against it (registers + broadcast smem reads), and the
-//   whole CTA applies the rank-32 Hermitian update to the trailing triangle
+//   for each 32-column block:   ALL threads eliminate the 32x32 diagonal block in
+//   shared memory with one barrier per column (trailing entries use the unscaled
+//   column and 1/d; the scaled column goes to a second array), every thread then
+//   solves one row of the panel below against it (a 32-step dependency chain), and
+//   the whole CTA applies the rank-32 Hermitian update to the trailing triangle
 //   from a shared-memory copy of the panel (double: 32x32 blocks per warp on the
-//   FP64 tensor pipe, DMMA.8x8x4 -- same flop rate as DFMA on this part but a
-//   quarter of the shared-memory loads, which is what bounds the scalar form).
+//   FP64 tensor pipe, DMMA.8x8x4 -- a quarter of the shared-memory loads of the
+//   scalar form, which is what bounds it).  n = 256 double: 0.18 ms.  (Round 1's
+//   first version factored the diagonal block in one warp's registers with shuffles:
+//   2000 clocks per column, instruction-latency bound.)
 // Upper storage is handled as the conjugate-transposed view of the same
 // lower algorithm (U = L^H), so the other triangle is never referenced, as in
 // the reference.  Same arithmetic as the reference per column: alpha = sqrt(a_jj),

@@ -10,7 +10,15 @@ namespace El {
 template <typename F> void Cholesky(UpperOrLower uplo, Matrix<F>& A);
 template <typename F> void Cholesky(UpperOrLower uplo, AbstractDistMatrix<F>& A, bool scalapack = false);
 
+// Reverse factorisations A = L^H L (LOWER) / A = U U^H (UPPER), src/lapack_like/factor/Cholesky.cpp:55-141
+// (cholesky::ReverseLowerVariant3Blocked / ReverseUpperVariant3Blocked)
+template <typename F> void ReverseCholesky(UpperOrLower uplo, Matrix<F>& A);
+template <typename F> void ReverseCholesky(UpperOrLower uplo, AbstractDistMatrix<F>& A);
+
 namespace cholesky {
+// the left-looking blocked variants (Cholesky/LowerVariant2.hpp:43-110, UpperVariant2.hpp); same factor as Cholesky()
+template <typename F> void LowerVariant2Blocked(AbstractDistMatrix<F>& A);
+template <typename F> void UpperVariant2Blocked(AbstractDistMatrix<F>& A);
 // A holds a Cholesky factor; B := inv(A) B (or the transposed system), SolveAfter.hpp:78-107
 template <typename F>
 void SolveAfter(UpperOrLower uplo, Orientation orientation, const AbstractDistMatrix<F>& A, AbstractDistMatrix<F>& B);

@@ -102,6 +102,13 @@ template <typename T>
 void Trmm(LeftOrRight side, UpperOrLower uplo, Orientation orientation, UnitOrNonUnit diag, T alpha,
           const AbstractDistMatrix<T>& A, AbstractDistMatrix<T>& B);
 
+// ---- TwoSidedTrsm / TwoSidedTrmm (src/blas_like/level3/TwoSidedTrsm.cpp:17-40, TwoSidedTrmm.cpp:18-42) ----
+// A := inv(L) A inv(L)^H | inv(U)^H A inv(U)   resp.   A := L^H A L | U A U^H on the `uplo` triangle of Hermitian A
+template <typename F>
+void TwoSidedTrsm(UpperOrLower uplo, UnitOrNonUnit diag, AbstractDistMatrix<F>& A, const AbstractDistMatrix<F>& B);
+template <typename F>
+void TwoSidedTrmm(UpperOrLower uplo, UnitOrNonUnit diag, AbstractDistMatrix<F>& A, const AbstractDistMatrix<F>& B);
+
 // ---- Trsm (src/blas_like/level3/Trsm.cpp:24-398, Trsm/{LLN,LLT,LUN,LUT,RLN,RLT,RUN,RUT}.hpp) ----
 template <typename F>
 void Trsm(LeftOrRight side, UpperOrLower uplo, Orientation orientation, UnitOrNonUnit diag, F alpha,

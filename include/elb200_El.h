@@ -178,6 +178,11 @@ ElError ElRedistStats(uint64_t out[8], bool reset);
     ElError ElSyr2kDist_##SUF(ElUpperOrLower uplo, ElOrientation orientation, SCALAR alpha,                 \
                               ElConstDistMatrix_##SUF A, ElConstDistMatrix_##SUF B, SCALAR beta,            \
                               ElDistMatrix_##SUF C);                                                        \
+    /* ElTwoSidedTrsmDist / ElTwoSidedTrmmDist (include/El/blas_like/level3.h) */                          \
+    ElError ElTwoSidedTrsmDist_##SUF(ElUpperOrLower uplo, ElUnitOrNonUnit diag, ElDistMatrix_##SUF A,       \
+                                     ElConstDistMatrix_##SUF B);                                            \
+    ElError ElTwoSidedTrmmDist_##SUF(ElUpperOrLower uplo, ElUnitOrNonUnit diag, ElDistMatrix_##SUF A,       \
+                                     ElConstDistMatrix_##SUF B);                                            \
     /* ElTrr2kDist (include/El/blas_like/level3.h): E_tri := alpha op(A) op(B) + beta op(C) op(D) + gamma E_tri */ \
     ElError ElTrr2kDist_##SUF(ElUpperOrLower uplo, ElOrientation orientA, ElOrientation orientB,            \
                               ElOrientation orientC, ElOrientation orientD, SCALAR alpha,                   \
@@ -189,6 +194,10 @@ ElError ElRedistStats(uint64_t out[8], bool reset);
                              ElDistMatrix_##SUF B);                                                         \
     /* factor / solve */                                                                                    \
     ElError ElCholeskyDist_##SUF(ElUpperOrLower uplo, ElDistMatrix_##SUF A);                                \
+    /* ElReverseCholeskyDist (include/El/lapack_like/factor.h): A = L^H L / U U^H; the left-looking variant 2 */ \
+    /* (cholesky::{Lower,Upper}Variant2Blocked) has no C name in the reference: exposed for the tests          */ \
+    ElError ElReverseCholeskyDist_##SUF(ElUpperOrLower uplo, ElDistMatrix_##SUF A);                         \
+    ElError ElCholeskyVariant2Dist_##SUF(ElUpperOrLower uplo, ElDistMatrix_##SUF A);                        \
     ElError ElCholeskySolveAfterDist_##SUF(ElUpperOrLower uplo, ElOrientation orientation,                  \
                                            ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B);                \
     ElError ElHPDSolveDist_##SUF(ElUpperOrLower uplo, ElOrientation orientation, ElConstDistMatrix_##SUF A, \

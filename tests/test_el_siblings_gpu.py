@@ -138,3 +138,71 @@ def test_trr2k_all_orientation_cases(El, dt):
                         assert np.array_equal(got[~mask], E0[~mask]), (dt, uplo, oa, ob, oc, od)
                         bound = 8 * k * e * (np.linalg.norm(A) * np.linalg.norm(B) + np.linalg.norm(Cc) * np.linalg.norm(D) + np.linalg.norm(E0))
                         assert np.linalg.norm(got - want) <= bound, (dt, uplo, oa, ob, oc, od)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128])
+def test_two_sided_trsm_trmm(El, dt):
+    """El::TwoSidedTrsm / TwoSidedTrmm (TwoSidedTrsm/{LVar4,UVar4}.hpp, TwoSidedTrmm/*.hpp): only the `uplo` triangle
+    of the Hermitian A is read and written; the other triangle stays bit-identical."""
+    n, nb = 140, 32
+    S = O.fill(1, n, n, 5, diag=float(n), dtype=dt)          # Hermitian, well conditioned
+    Tfull = np.asfortranarray((O.fill(0, n, n, 7, dtype=dt) / n + 2 * np.eye(n)).astype(dt))
+    junk = O.fill(0, n, n, 9, dtype=dt)
+    e = np.finfo(np.float64).eps
+    for uplo in "LU":
+        mask = O._tri_mask(n, n, uplo)
+        A0 = np.where(mask, S, junk)                          # garbage in the triangle that must not be referenced
+        for diag in "NU":
+            T = O._tri(Tfull, uplo, diag)
+            Ti = np.linalg.inv(T)
+            for solve in (True, False):
+                dA = _dm(El, np.asfortranarray(A0))
+                El.PushBlocksizeStack(nb)
+                (El.TwoSidedTrsm if solve else El.TwoSidedTrmm)(UL[uplo], DG[diag], dA, _dm(El, Tfull))
+                El.PopBlocksizeStack()
+                if solve:
+                    full = Ti @ S @ Ti.conj().T if uplo == "L" else Ti.conj().T @ S @ Ti
+                else:
+                    full = T.conj().T @ S @ T if uplo == "L" else T @ S @ T.conj().T
+                got = dA.ToGlobal()
+                assert np.array_equal(got[~mask], A0[~mask]), (dt, uplo, diag, solve)
+                err = np.linalg.norm((got - full)[mask])
+                assert err <= 200 * n * e * np.linalg.norm(full) * (np.linalg.cond(T) if solve else 1.0), (dt, uplo, diag, solve, err)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128, np.float32])
+def test_reverse_cholesky_and_variant2(El, dt):
+    """SURVEY 8f rank 3: El::ReverseCholesky (A = L^H L / U U^H, Cholesky/ReverseLowerVariant3.hpp:73-126,
+    ReverseUpperVariant3.hpp:75-123) and the left-looking cholesky::{Lower,Upper}Variant2Blocked
+    (LowerVariant2.hpp:43-110).  Residual ||A - F^H F|| / (n eps ||A||) <= 10 as for Cholesky; the triangle that is
+    not referenced stays bit-identical; variant 2 agrees with variant 3."""
+    n, nb = 150, 32
+    A = O.fill(1, n, n, 5, diag=float(n), dtype=dt)
+    junk = O.fill(0, n, n, 9, dtype=dt)
+    e = np.finfo(np.dtype(dt).type(0).real.dtype).eps
+    for uplo in "LU":
+        mask = O._tri_mask(n, n, uplo)
+        A0 = np.asfortranarray(np.where(mask, A, junk))
+        dA = _dm(El, A0)
+        El.PushBlocksizeStack(nb)
+        El.ReverseCholesky(UL[uplo], dA)
+        got = dA.ToGlobal()
+        assert np.array_equal(got[~mask], A0[~mask]), (dt, uplo)
+        F = np.where(mask, got, 0)
+        rec = F.conj().T @ F if uplo == "L" else F @ F.conj().T
+        assert np.linalg.norm(rec - A) / (n * e * np.linalg.norm(A)) <= 10, (dt, uplo)
+        d3, d2 = _dm(El, A0), _dm(El, A0)
+        El.Cholesky(UL[uplo], d3)
+        El.CholeskyVariant2(UL[uplo], d2)
+        El.PopBlocksizeStack()
+        g3, g2 = d3.ToGlobal(), d2.ToGlobal()
+        # variant 2 updates the FULL diagonal block (AxpyContract of X11, LowerVariant2.hpp:88-90), as the reference
+        # does, so the other triangle of the diagonal blocks is not preserved; off-diagonal blocks are
+        other_blocks = ~mask & (np.add.outer(np.arange(n) // nb, -(np.arange(n) // nb)) != 0)
+        assert np.array_equal(g2[other_blocks], A0[other_blocks])
+        assert O.cholesky_residual(uplo, g2, A) <= 10
+        assert np.linalg.norm((g2 - g3)[mask]) <= 50 * n * e * np.linalg.norm(g3[mask])
+    bad = A.copy(order="F")
+    bad[40, 40] = -1.0
+    with pytest.raises(El.NonHPDMatrixException):
+        El.ReverseCholesky(0, _dm(El, bad))
