@@ -41,7 +41,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=32768, help="m=n=k of the DGEMM workload")
+    ap.add_argument("--n", "--size", dest="n", type=int, default=32768,
+                    help="m=n=k of the DGEMM workload (--size under torchrun, whose own parser claims --n)")
     ap.add_argument("--nb", type=int, default=128)
     ap.add_argument("--potrf-n", type=int, default=65536)
     ap.add_argument("--potrf-nb", type=int, default=256)

@@ -162,6 +162,11 @@ void gemm_device<c64_t>(int mode, char ta, char tb, i64 m, i64 n, i64 k, c64_t a
                         i64 gis, i64 gj0, i64 gjs, cudaStream_t s) {
     zgemm_device(mode, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, gi0, gis, gj0, gjs, s);
 }
+bool sgemm_ffma_device(int mode, bool ta, bool tb, i64 m, i64 n, i64 k, float alpha, const float* A, i64 lda,
+                       const float* B, i64 ldb, float beta, float* C, i64 ldc, i64 gi0, i64 gis, i64 gj0, i64 gjs,
+                       cudaStream_t s);
+int g_sgemm_ffma_path = 0;   // 0 automatic, 1 always the generic SIMT kernel (elb200_sgemm_set_ffma_path)
+int g_sgemm_ffma_last = 0;   // 1 generic SIMT kernel, 2 register-tiled float kernel
 template <>
 void gemm_device<float>(int mode, char ta, char tb, i64 m, i64 n, i64 k, float alpha, const float* A,
                         i64 lda, const float* B, i64 ldb, float beta, float* C, i64 ldc, i64 gi0,
@@ -172,6 +177,17 @@ void gemm_device<float>(int mode, char ta, char tb, i64 m, i64 n, i64 k, float a
         sgemm_3xtf32_device(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, s))
         return;
     sgemm_note_simt();
+    // exact FFMA: the register-tiled float kernel (gemm_f32_ffma.cu) whenever the operands allow 16-byte loads,
+    // the generic SIMT kernel of this file otherwise
+    {
+        const char ua = up(ta), ub = up(tb);
+        if (g_sgemm_ffma_path != 1 && k > 0 &&
+            sgemm_ffma_device(mode, ua != 'N', ub != 'N', m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, gi0, gis, gj0, gjs, s)) {
+            g_sgemm_ffma_last = 2;
+            return;
+        }
+    }
+    g_sgemm_ffma_last = 1;
     gemm_simt_device<float>(mode, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, gi0, gis, gj0, gjs, s);
 }
 template <>
@@ -297,3 +313,10 @@ int elb200_csyrk(char uplo, char trans, int64_t n, int64_t k, elb200_c32 alpha, 
 }
 
 }  // extern "C"
+
+extern "C" {
+// exact-FFMA float path: 0 automatic (register-tiled kernel when the operands allow 16-byte loads), 1 always the
+// generic SIMT kernel; which one the last exact-FFMA call used: 1 generic, 2 register-tiled
+void elb200_sgemm_set_ffma_path(int p) { elb200::g_sgemm_ffma_path = p; }
+int elb200_sgemm_ffma_last_kernel(void) { return elb200::g_sgemm_ffma_last; }
+}

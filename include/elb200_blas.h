@@ -109,6 +109,10 @@ int elb200_sgemm_3xtf32(char transA, char transB, int64_t m, int64_t n, int64_t 
  * (default), 1 = 3xTF32 on tcgen05 whenever the operands are 16-byte aligned with ld % 4 == 0
  * (otherwise, and for the masked TRRK form, exact FFMA).  elb200_sgemm_last_kernel: 1 SIMT, 2 tcgen05. */
 void elb200_sgemm_set_mode(int mode);
+/* exact-FFMA path: 0 automatic (register-tiled kernel gemm_f32_ffma.cu when A, B are 16-byte aligned with
+ * ld % 4 == 0), 1 always the generic SIMT kernel; last_kernel: 1 generic, 2 register-tiled */
+void elb200_sgemm_set_ffma_path(int path);
+int elb200_sgemm_ffma_last_kernel(void);
 int elb200_sgemm_get_mode(void);
 int elb200_sgemm_last_kernel(void);
 
