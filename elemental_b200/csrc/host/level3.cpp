@@ -178,6 +178,14 @@ void SummaC(Orientation oA, Orientation oB, T alpha, const AbstractDistMatrix<T>
     int reserve = g.P2P().on ? 0 : dev::PanelSms(8);
     if (const char* e = std::getenv("ELB200_SUMMA_PANEL_SMS")) reserve = std::atoi(e);
     const int gemmSms = reserve > 0 ? std::max(1, elb200::sm_count() - reserve) : 0;
+    // Panels are gathered SUMMA_BATCH (default 4) k-steps at a time -- one redistribution of a (batch x Blocksize())
+    // wide panel instead of `batch` narrow ones -- and consumed by `batch` local rank-Blocksize() updates on views
+    // of it: every entry of C still receives the same updates in the same order (bit-identical), but the latency
+    // chain of a redistribution (pushes, flags, unpack) is paid once per batch.  That chain is what bounds SUMMA-C
+    // once the local update of one step is short (8 GPUs; the column bands of GemmHost).
+    Int batch = 4;
+    if (const char* e = std::getenv("ELB200_SUMMA_BATCH")) batch = std::max(1, std::atoi(e));
+    const Int wide = batch * bsize;
     AbstractDistMatrix<T> A1[2] = {AbstractDistMatrix<T>(g, MC, STAR), AbstractDistMatrix<T>(g, MC, STAR)};
     AbstractDistMatrix<T> B1[2] = {AbstractDistMatrix<T>(g, STAR, MR), AbstractDistMatrix<T>(g, STAR, MR)};
     dev::Event ready[2], freed[2], fork;
@@ -185,20 +193,25 @@ void SummaC(Orientation oA, Orientation oB, T alpha, const AbstractDistMatrix<T>
     fork.Record(mainS);   // A, B (and the scaled C) are final on the main stream from here on
     fork.Wait(panelS);
     Int it = 0;
-    for (Int k = 0; k < sumDim; k += bsize, ++it) {
-        const Int nb = std::min(bsize, sumDim - k);
+    for (Int k = 0; k < sumDim; k += wide, ++it) {
+        const Int kw = std::min(wide, sumDim - k);
         const int slot = (int)(it & 1);
         {
             dev::StreamScope onPanel(panelS);
             if (it >= 2) freed[slot].Wait(panelS);
-            FormPanel(oA, A, 0, k, m, nb, A1[slot]);
-            FormPanel(oB, B, k, 0, nb, n, B1[slot]);
+            FormPanel(oA, A, 0, k, m, kw, A1[slot]);
+            FormPanel(oB, B, k, 0, kw, n, B1[slot]);
             ready[slot].Record(panelS);
         }
         ready[slot].Wait(mainS);
         {
             dev::SmLimitScope lim(gemmSms);
-            LocalGemm(NORMAL, NORMAL, alpha, A1[slot], B1[slot], T(1), C);
+            for (Int j = 0; j < kw; j += bsize) {
+                const Int nb = std::min(bsize, kw - j);
+                auto Av = LockedView(static_cast<const AbstractDistMatrix<T>&>(A1[slot]), 0, j, m, nb);
+                auto Bv = LockedView(static_cast<const AbstractDistMatrix<T>&>(B1[slot]), j, 0, nb, n);
+                LocalGemm(NORMAL, NORMAL, alpha, Av, Bv, T(1), C);
+            }
         }
         freed[slot].Record(mainS);
     }
