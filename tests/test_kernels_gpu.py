@@ -468,3 +468,114 @@ def test_trapezoid_kernels_on_the_global_staircase(dt):
                 check(L.elb200_make_trapezoidal(code, G.ch(uplo), G.i64(m), G.i64(n), dA.ptr, G.i64(dA.ld),
                                                 G.i64(rs), G.i64(rst), G.i64(cs), G.i64(cst), G.i64(off), G.stream()), "make")
                 assert np.array_equal(dA.get(), np.where(inside, A0, 0)) and dA.padding_untouched()
+
+
+def test_zgemm_real_kernel_path_agrees_with_complex_kernel():
+    """Complex<double> products above the size threshold run on the real persistent kernel through the (re, im) row-pair
+    identity (gemm_c64_real.cu); the dedicated complex kernel (gemm_c64.cu) is the second implementation.  Both must
+    meet the GEMM tolerance against numpy, on ragged sizes, every orientation, the masked TRRK form and ZHERK's real
+    diagonal, and elb200_zgemm_last_kernel must show that the intended kernel ran."""
+    import gpuutil as G
+    L = G.lib()
+    L.elb200_zgemm_last_kernel.restype = int
+    dt = np.complex128
+    rng = np.random.default_rng(21)
+    try:
+        for (m, n, k) in [(257, 129, 200), (130, 300, 77), (512, 256, 128)]:
+            for ta in "NTC":
+                for tb in "NTC":
+                    for alpha, beta in ((1.0, 1.0), (-1.0, 1.0), (0.5 - 2.0j, 0.25), (2.0, 0.5 + 1.0j)):
+                        A = G.rand(rng, *((m, k) if ta == "N" else (k, m)), dt)
+                        B = G.rand(rng, *((k, n) if tb == "N" else (n, k)), dt)
+                        C0 = G.rand(rng, m, n, dt)
+                        ref = alpha * (_op(A, ta) @ _op(B, tb)) + beta * C0
+                        tol = 4 * k * G.eps(dt) * np.linalg.norm(A) * np.linalg.norm(B) + 8 * G.eps(dt) * np.linalg.norm(C0) * abs(beta)
+                        for path, kern in ((0, 2), (1, 1)):
+                            L.elb200_zgemm_set_path(path)
+                            dA, dB, dC = G.DevMat(A, A.shape[0] + 3, offset=1), G.DevMat(B, B.shape[0] + 1), G.DevMat(C0, m + 5, offset=1)
+                            G.gemm(ta, tb, alpha, dA, dB, beta, dC, k)
+                            assert L.elb200_zgemm_last_kernel() == kern, (path, m, n, k)
+                            assert np.linalg.norm(dC.get() - ref) <= tol, (path, ta, tb, m, n, k, alpha, beta)
+                            assert dC.padding_untouched()
+        # masked rank-k update on a global staircase and the Hermitian update (real diagonal), both paths
+        m, n, k = 300, 260, 64
+        for uplo in "LU":
+            A = G.rand(rng, m, k, dt); B = G.rand(rng, k, n, dt); C0 = G.rand(rng, m, n, dt)
+            gi = 1 + 2 * np.arange(m)[:, None]; gj = 3 + 4 * np.arange(n)[None, :]
+            mask = gi >= gj if uplo == "L" else gi <= gj
+            full = -(A @ B) + C0
+            for path, kern in ((0, 2), (1, 1)):
+                L.elb200_zgemm_set_path(path)
+                dA, dB, dC = G.DevMat(A), G.DevMat(B, k + 2), G.DevMat(C0, m + 3)
+                G.trrk(uplo, "N", "N", -1.0, dA, dB, 1.0, dC, k, 1, 2, 3, 4)
+                assert L.elb200_zgemm_last_kernel() == kern
+                got = dC.get()
+                assert np.array_equal(got[~mask], C0[~mask])
+                assert np.linalg.norm((got - full)[mask]) <= 4 * k * G.eps(dt) * np.linalg.norm(A) * np.linalg.norm(B)
+            nn, kk = 300, 96
+            for tr in "NC":
+                A = G.rand(rng, *((nn, kk) if tr == "N" else (kk, nn)), dt)
+                C0 = G.rand(rng, nn, nn, dt)
+                ref = O.blas_herk(uplo, tr, -1.0, A, 1.0, C0.copy())
+                for path, kern in ((0, 2), (1, 1)):
+                    L.elb200_zgemm_set_path(path)
+                    dA, dC = G.DevMat(A), G.DevMat(C0, nn + 1)
+                    G.herk(uplo, tr, -1.0, dA, 1.0, dC, kk)
+                    assert L.elb200_zgemm_last_kernel() == kern
+                    got = dC.get()
+                    assert np.linalg.norm(got - ref) <= 4 * kk * G.eps(dt) * np.linalg.norm(A) ** 2
+                    tri = np.tril(np.ones((nn, nn), bool)) if uplo == "L" else np.triu(np.ones((nn, nn), bool))
+                    assert np.array_equal(got[~tri], C0[~tri])
+                    assert np.all(np.diag(got).imag == 0.0)
+    finally:
+        L.elb200_zgemm_set_path(0)
+
+
+def test_sgemm_register_tiled_ffma_kernel_agrees_with_generic_kernel():
+    """Exact-FFMA float products with 16-byte-aligned operands run on the register-tiled kernel (gemm_f32_ffma.cu); the
+    generic SIMT kernel (gemm_simt.cu) takes everything else.  Both against numpy in FP64, ragged sizes, all four
+    storage orientations, general alpha / beta, the masked form; unaligned operands must fall back (kernel 1)."""
+    import gpuutil as G
+    L = G.lib()
+    L.elb200_sgemm_ffma_last_kernel.restype = int
+    dt = np.float32
+    rng = np.random.default_rng(22)
+    try:
+        for (m, n, k) in [(128, 128, 8), (257, 131, 45), (130, 260, 200), (1, 1, 1), (5, 300, 17)]:
+            for ta in "NT":
+                for tb in "NT":
+                    for alpha, beta in ((1.0, 0.0), (-1.0, 1.0), (3.0, 4.0)):
+                        A = G.rand(rng, *((m, k) if ta == "N" else (k, m)), dt)
+                        B = G.rand(rng, *((k, n) if tb == "N" else (n, k)), dt)
+                        C0 = G.rand(rng, m, n, dt)
+                        ref = alpha * (_op(A, ta).astype(np.float64) @ _op(B, tb).astype(np.float64)) + beta * C0
+                        tol = 4 * k * G.eps(dt) * max(np.linalg.norm(A) * np.linalg.norm(B), 1) + 8 * G.eps(dt) * np.linalg.norm(C0) * abs(beta)
+                        lda = (A.shape[0] + 3) // 4 * 4 + 4; ldb = (B.shape[0] + 3) // 4 * 4
+                        for path, kern in ((0, 2), (1, 1)):
+                            L.elb200_sgemm_set_ffma_path(path)
+                            dA, dB, dC = G.DevMat(A, lda), G.DevMat(B, ldb), G.DevMat(C0, m + 5, offset=1)
+                            G.gemm(ta, tb, alpha, dA, dB, beta, dC, k)
+                            assert L.elb200_sgemm_ffma_last_kernel() == kern, (path, m, n, k)
+                            assert np.linalg.norm(dC.get() - ref) <= tol, (path, ta, tb, m, n, k, alpha, beta)
+                            assert dC.padding_untouched()
+        L.elb200_sgemm_set_ffma_path(0)
+        # unaligned leading dimension / base pointer: the generic kernel, silently and correctly
+        A = G.rand(rng, 130, 40, dt); B = G.rand(rng, 40, 70, dt); C0 = G.rand(rng, 130, 70, dt)
+        dA, dB, dC = G.DevMat(A, 133, offset=1), G.DevMat(B, 41), G.DevMat(C0, 131)
+        G.gemm("N", "N", 1.0, dA, dB, 1.0, dC, 40)
+        assert L.elb200_sgemm_ffma_last_kernel() == 1
+        assert np.linalg.norm(dC.get() - (A.astype(np.float64) @ B + C0)) <= 4 * 40 * G.eps(dt) * np.linalg.norm(A) * np.linalg.norm(B)
+        # masked form on the register-tiled kernel
+        m, n, k = 260, 200, 32
+        for uplo in "LU":
+            A = G.rand(rng, m, k, dt); B = G.rand(rng, k, n, dt); C0 = G.rand(rng, m, n, dt)
+            gi = 2 * np.arange(m)[:, None]; gj = 1 + 3 * np.arange(n)[None, :]
+            mask = gi >= gj if uplo == "L" else gi <= gj
+            dA, dB, dC = G.DevMat(A), G.DevMat(B), G.DevMat(C0, m + 4)
+            G.trrk(uplo, "N", "N", -1.0, dA, dB, 1.0, dC, k, 0, 2, 1, 3)
+            assert L.elb200_sgemm_ffma_last_kernel() == 2
+            got = dC.get()
+            assert np.array_equal(got[~mask], C0[~mask])
+            assert np.linalg.norm((got - (C0 - A.astype(np.float64) @ B))[mask]) <= 4 * k * G.eps(dt) * np.linalg.norm(A) * np.linalg.norm(B)
+    finally:
+        L.elb200_sgemm_set_ffma_path(0)
