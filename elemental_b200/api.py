@@ -550,6 +550,90 @@ def CholeskySolveAfter(uplo, orient, A: DistMatrix, B: DistMatrix):
     _check(_same(A, B)._fn("ElCholeskySolveAfterDist")(uplo, orient, A._h, B._h), "ElCholeskySolveAfterDist")
 
 
+class DistPermutation:
+    """El::DistPermutation (include/El/core/DistPermutation.hpp): a swap sequence whose list lives in device memory.
+    Row i of P A is row Preimage(i) of A."""
+
+    def __init__(self, grid: Grid | None = None):
+        self.grid = grid if grid is not None else default_grid()
+        self._h = C.c_void_p()
+        _check(lib().ElDistPermutationCreate(C.byref(self._h), self.grid._h), "ElDistPermutationCreate")
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().ElDistPermutationDestroy(self._h)
+        except Exception:
+            pass
+
+    def _geti(self, fn, *args):
+        v = C.c_int()
+        _check(getattr(lib(), fn)(self._h, *args, C.byref(v)), fn)
+        return v.value
+
+    def _getb(self, fn):
+        v = C.c_bool()
+        _check(getattr(lib(), fn)(self._h, C.byref(v)), fn)
+        return bool(v.value)
+
+    def Empty(self): _check(lib().ElDistPermutationEmpty(self._h), "ElDistPermutationEmpty")
+    def MakeIdentity(self, size): _sync_stream(); _check(lib().ElDistPermutationMakeIdentity(self._h, int(size)), "MakeIdentity")
+    def ReserveSwaps(self, n): _sync_stream(); _check(lib().ElDistPermutationReserveSwaps(self._h, int(n)), "ReserveSwaps")
+    def Swap(self, origin, dest): _sync_stream(); _check(lib().ElDistPermutationSwap(self._h, int(origin), int(dest)), "Swap")
+
+    def SwapSequence(self, P: "DistPermutation", offset=0):
+        _sync_stream()
+        _check(lib().ElDistPermutationSwapSequence(self._h, P._h, int(offset)), "SwapSequence")
+
+    def Height(self): return self._geti("ElDistPermutationHeight")
+    def Width(self): return self._geti("ElDistPermutationWidth")
+    def Parity(self): _sync_stream(); return self._getb("ElDistPermutationParity")
+    def IsSwapSequence(self): return self._getb("ElDistPermutationIsSwapSequence")
+    def IsImplicitSwapSequence(self): return self._getb("ElDistPermutationIsImplicitSwapSequence")
+    def Image(self, origin): _sync_stream(); return self._geti("ElDistPermutationImage", int(origin))
+    def Preimage(self, dest): _sync_stream(); return self._geti("ElDistPermutationPreimage", int(dest))
+
+    def Preimages(self) -> np.ndarray:
+        _sync_stream()
+        n = self.Height()
+        out = np.zeros(max(n, 1), dtype=np.int32)
+        _check(lib().ElDistPermutationPreimages(self._h, out.ctypes.data_as(C.c_void_p)), "ElDistPermutationPreimages")
+        return out[:n].astype(np.int64)
+
+    def _apply(self, name, A: DistMatrix, offset):
+        _sync_stream()
+        _check(A._fn(name)(self._h, A._h, int(offset)), name)
+
+    def PermuteRows(self, A, offset=0): self._apply("ElDistPermutationPermuteRowsDist", A, offset)
+    def InversePermuteRows(self, A, offset=0): self._apply("ElDistPermutationInversePermuteRowsDist", A, offset)
+    def PermuteCols(self, A, offset=0): self._apply("ElDistPermutationPermuteColsDist", A, offset)
+    def InversePermuteCols(self, A, offset=0): self._apply("ElDistPermutationInversePermuteColsDist", A, offset)
+
+
+def LU(A: DistMatrix, P: DistPermutation | None = None):
+    """El::LU(A) without pivoting / El::LU(A, P) with partial pivoting (src/lapack_like/factor/LU.cpp:21-220)."""
+    _sync_stream()
+    if P is None:
+        _check(A._fn("ElLUDist")(A._h), "ElLUDist")
+    else:
+        _check(A._fn("ElLUPartialPivDist")(A._h, P._h), "ElLUPartialPivDist")
+
+
+def LUSolveAfter(orient, A: DistMatrix, B: DistMatrix, P: DistPermutation | None = None):
+    """lu::SolveAfter(orientation, A, [P,] B) (LU/SolveAfter.hpp)."""
+    _sync_stream()
+    if P is None:
+        _check(_same(A, B)._fn("ElSolveAfterLUDist")(orient, A._h, B._h), "ElSolveAfterLUDist")
+    else:
+        _check(_same(A, B)._fn("ElSolveAfterLUPartialPivDist")(orient, A._h, P._h, B._h), "ElSolveAfterLUPartialPivDist")
+
+
+def LinearSolve(A: DistMatrix, B: DistMatrix):
+    """El::LinearSolve(A, B) (src/lapack_like/solve/Linear.cpp): B := inv(A) B, A unchanged."""
+    _sync_stream()
+    _check(_same(A, B)._fn("ElLinearSolveDist")(A._h, B._h), "ElLinearSolveDist")
+
+
 def HPDSolve(uplo, orient, A: DistMatrix, B: DistMatrix):
     """El::HPDSolve(uplo, orientation, A, B) (src/lapack_like/solve/HPD.cpp:59-69)."""
     _sync_stream()

@@ -6,6 +6,7 @@
 #include "dev.hpp"
 #include "elb200/factor.hpp"
 #include "elb200/io.hpp"
+#include "elb200/lu.hpp"
 #include "elb200_El.h"
 
 using namespace El;
@@ -92,6 +93,37 @@ ElError ElGridRow(ElConstGrid g, int* v) { return Try([&] { *v = G(g)->Row(); })
 ElError ElGridCol(ElConstGrid g, int* v) { return Try([&] { *v = G(g)->Col(); }); }
 ElError ElGridVCRank(ElConstGrid g, int* v) { return Try([&] { *v = G(g)->VCRank(); }); }
 ElError ElGridVRRank(ElConstGrid g, int* v) { return Try([&] { *v = G(g)->VRRank(); }); }
+
+static inline DistPermutation* PM(ElDistPermutation P) { return reinterpret_cast<DistPermutation*>(P); }
+static inline const DistPermutation* CPM(ElConstDistPermutation P) { return reinterpret_cast<const DistPermutation*>(P); }
+ElError ElDistPermutationCreate(ElDistPermutation* P, ElConstGrid g) {
+    return Try([&] { *P = reinterpret_cast<ElDistPermutation>(new DistPermutation(*G(g))); });
+}
+ElError ElDistPermutationDestroy(ElConstDistPermutation P) { return Try([&] { delete CPM(P); }); }
+ElError ElDistPermutationEmpty(ElDistPermutation P) { return Try([&] { PM(P)->Empty(); }); }
+ElError ElDistPermutationMakeIdentity(ElDistPermutation P, ElInt size) { return Try([&] { PM(P)->MakeIdentity(size); }); }
+ElError ElDistPermutationReserveSwaps(ElDistPermutation P, ElInt maxSwaps) { return Try([&] { PM(P)->ReserveSwaps(maxSwaps); }); }
+ElError ElDistPermutationSwap(ElDistPermutation P, ElInt origin, ElInt dest) { return Try([&] { PM(P)->Swap(origin, dest); }); }
+ElError ElDistPermutationSwapSequence(ElDistPermutation P, ElConstDistPermutation PAppend, ElInt offset) {
+    return Try([&] { PM(P)->SwapSequence(*CPM(PAppend), offset); });
+}
+ElError ElDistPermutationHeight(ElConstDistPermutation P, ElInt* h) { return Try([&] { *h = CPM(P)->Height(); }); }
+ElError ElDistPermutationWidth(ElConstDistPermutation P, ElInt* w) { return Try([&] { *w = CPM(P)->Width(); }); }
+ElError ElDistPermutationParity(ElConstDistPermutation P, bool* parity) { return Try([&] { *parity = CPM(P)->Parity(); }); }
+ElError ElDistPermutationIsSwapSequence(ElConstDistPermutation P, bool* b) { return Try([&] { *b = CPM(P)->IsSwapSequence(); }); }
+ElError ElDistPermutationIsImplicitSwapSequence(ElConstDistPermutation P, bool* b) {
+    return Try([&] { *b = CPM(P)->IsImplicitSwapSequence(); });
+}
+ElError ElDistPermutationImage(ElConstDistPermutation P, ElInt origin, ElInt* dest) { return Try([&] { *dest = CPM(P)->Image(origin); }); }
+ElError ElDistPermutationPreimage(ElConstDistPermutation P, ElInt dest, ElInt* origin) {
+    return Try([&] { *origin = CPM(P)->Preimage(dest); });
+}
+ElError ElDistPermutationPreimages(ElConstDistPermutation P, ElInt* out) {
+    return Try([&] {
+        const std::vector<Int> v = CPM(P)->Preimages();
+        std::copy(v.begin(), v.end(), out);
+    });
+}
 
 ElError ElSetGemmDotBlocksize(ElInt b) { return Try([&] { SetGemmDotBlocksize(b); }); }
 ElError ElRedistStats(uint64_t out[8], bool reset) {
@@ -305,6 +337,32 @@ ElError ElRedistStats(uint64_t out[8], bool reset) {
     ElError ElHPDSolveDist_##SUF(ElUpperOrLower uplo, ElOrientation o, ElConstDistMatrix_##SUF A,                  \
                                  ElDistMatrix_##SUF B) {                                                           \
         return Try([&] { HPDSolve(UL(uplo), O(o), *CM_##SUF(A), *M_##SUF(B)); });                                  \
+    }                                                                                                              \
+    ElError ElLUDist_##SUF(ElDistMatrix_##SUF A) { return Try([&] { LU(*M_##SUF(A)); }); }                         \
+    ElError ElLUPartialPivDist_##SUF(ElDistMatrix_##SUF A, ElDistPermutation P) {                                  \
+        return Try([&] { LU(*M_##SUF(A), *PM(P)); });                                                              \
+    }                                                                                                              \
+    ElError ElSolveAfterLUDist_##SUF(ElOrientation o, ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B) {           \
+        return Try([&] { lu::SolveAfter(O(o), *CM_##SUF(A), *M_##SUF(B)); });                                      \
+    }                                                                                                              \
+    ElError ElSolveAfterLUPartialPivDist_##SUF(ElOrientation o, ElConstDistMatrix_##SUF A, ElConstDistPermutation P, \
+                                               ElDistMatrix_##SUF B) {                                             \
+        return Try([&] { lu::SolveAfter(O(o), *CM_##SUF(A), *CPM(P), *M_##SUF(B)); });                             \
+    }                                                                                                              \
+    ElError ElLinearSolveDist_##SUF(ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B) {                             \
+        return Try([&] { LinearSolve(*CM_##SUF(A), *M_##SUF(B)); });                                               \
+    }                                                                                                              \
+    ElError ElDistPermutationPermuteRowsDist_##SUF(ElConstDistPermutation P, ElDistMatrix_##SUF A, ElInt off) {    \
+        return Try([&] { CPM(P)->PermuteRows(*M_##SUF(A), off); });                                                \
+    }                                                                                                              \
+    ElError ElDistPermutationInversePermuteRowsDist_##SUF(ElConstDistPermutation P, ElDistMatrix_##SUF A, ElInt off) { \
+        return Try([&] { CPM(P)->InversePermuteRows(*M_##SUF(A), off); });                                         \
+    }                                                                                                              \
+    ElError ElDistPermutationPermuteColsDist_##SUF(ElConstDistPermutation P, ElDistMatrix_##SUF A, ElInt off) {    \
+        return Try([&] { CPM(P)->PermuteCols(*M_##SUF(A), off); });                                                \
+    }                                                                                                              \
+    ElError ElDistPermutationInversePermuteColsDist_##SUF(ElConstDistPermutation P, ElDistMatrix_##SUF A, ElInt off) { \
+        return Try([&] { CPM(P)->InversePermuteCols(*M_##SUF(A), off); });                                         \
     }
 
 ELB200_DEFINE_TYPE(s, float, float, float)

@@ -379,7 +379,12 @@ void Matrix<T>::Empty(bool freeMemory) {
 }
 
 template <typename T>
-void Matrix<T>::Resize(Int h, Int w) { Resize(h, w, PaddedLDim<T>(h)); }
+void Matrix<T>::Resize(Int h, Int w) {
+    // Matrix/impl.hpp:698-717: the leading dimension changes only when the buffer has to grow ("simply shrink our
+    // view if possible"), so the leading h x w block survives a shrink
+    if (owner_ && data_ && h >= 0 && w >= 0 && h <= ldim_ && w <= width_) { height_ = h; width_ = w; return; }
+    Resize(h, w, PaddedLDim<T>(h));
+}
 
 template <typename T>
 void Matrix<T>::Resize(Int h, Int w, Int ld) {

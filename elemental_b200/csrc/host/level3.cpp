@@ -122,10 +122,9 @@ void LocalGemm(Orientation oA, Orientation oB, T alpha, const AbstractDistMatrix
 template <typename T>
 void LocalGemm(Orientation oA, Orientation oB, T alpha, const AbstractDistMatrix<T>& A,
                const AbstractDistMatrix<T>& B, AbstractDistMatrix<T>& C) {
-    // output takes the row distribution of op(A)'s rows and column distribution of op(B)'s columns
+    // Gemm.cpp:247-259: Resize, Zero, multiply -- the caller has aligned C (the beta form checks conformity)
     const Int m = (oA == NORMAL) ? A.Height() : A.Width();
     const Int n = (oB == NORMAL) ? B.Width() : B.Height();
-    if (oA == NORMAL) C.AlignColsWith(A, true, true); else C.AlignColsWith(A, true, true);
     C.Resize(m, n);
     Zero(C);
     LocalGemm(oA, oB, alpha, A, B, T(0), C);

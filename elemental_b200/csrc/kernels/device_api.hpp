@@ -47,6 +47,25 @@ void trsm_device(char side, char uplo, char trans, char diag, i64 m, i64 n, T al
 template <class T>
 void potrf_device(char uplo, i64 n, T* A, i64 lda, int* info_dev, i64 col_offset, cudaStream_t s);
 
+// LU panel and row interchanges (lu.cu).  getrf_panel: in-place LU of an m x n panel (m >= n <= 512) by one cooperative
+// kernel; ipiv[j] (device) = row of the panel exchanged with row j; info_dev set to col0 + j + 1 at the first zero pivot.
+template <class T>
+void getrf_panel_device(i64 m, i64 n, T* A, i64 lda, i64* ipiv, bool pivot, int* info_dev, i64 col0, cudaStream_t s);
+// slots of the rows a panel's swaps touch: slotRow[2 nb] (global row or -1), srcSlot[2 nb] (whose original row lands here)
+void swap_plan_device(int nb, const i64* ipiv, i64 k, i64* slotRow, int* srcSlot, cudaStream_t s);
+template <class T>
+void pack_rows_device(int S, const i64* slotRow, const int* srcSlot, const T* A, i64 lda, i64 ncols, int align, int stride,
+                      int rank, int shift, T* buf, cudaStream_t s);
+template <class T>
+void unpack_rows_device(int S, const i64* slotRow, const int* srcSlot, T* A, i64 lda, i64 ncols, int align, int stride,
+                        int rank, int shift, const T* all, i64 perRank, cudaStream_t s);
+// dst(iLoc, c) := src(perm[shift + iLoc stride], c) (rowwise) or dst(i, cLoc) := src(i, perm[shift + cLoc stride])
+template <class T>
+void permute_device(bool rowwise, i64 mloc, i64 nloc, const i64* perm, int shift, int stride, const T* src, i64 lds, T* dst,
+                    i64 ldd, cudaStream_t s);
+// origins[at + j] = offset + j, dests[at + j] = offset + ipiv[j]
+void append_swaps_device(i64* origins, i64* dests, i64 at, const i64* ipiv, int count, i64 offset, cudaStream_t s);
+
 // dst (op)= alpha*op(src) on one strided block (level1.cu)
 template <class T>
 void lattice_copy_device(const T* src, T* dst, i64 nrows, i64 ncols, i64 s_off, i64 s_rs, i64 s_cs,

@@ -6,3 +6,4 @@
 #include "elb200/level3.hpp"
 #include "elb200/factor.hpp"
 #include "elb200/io.hpp"
+#include "elb200/lu.hpp"

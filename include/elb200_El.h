@@ -61,6 +61,27 @@ ElError ElPushBlocksizeStack(ElInt blocksize);
 ElError ElPopBlocksizeStack(void);
 /* edge of the C blocks of SUMMA_Dot (reference: blockSizeDot = 2000 hard-coded, Gemm/NN.hpp:233);
  * 0 = sized for HBM (default).  Results do not depend on it. */
+/* DistPermutation (include/El/core/Permutation.h:49-160): a swap sequence; row i of P A is row Preimage(i) of A.
+ * The swap list is device-resident (a factorisation appends its pivots without a host round trip).            */
+typedef struct ElDistPermutationDummy* ElDistPermutation;
+typedef const struct ElDistPermutationDummy* ElConstDistPermutation;
+ElError ElDistPermutationCreate(ElDistPermutation* P, ElConstGrid g);
+ElError ElDistPermutationDestroy(ElConstDistPermutation P);
+ElError ElDistPermutationEmpty(ElDistPermutation P);
+ElError ElDistPermutationMakeIdentity(ElDistPermutation P, ElInt size);
+ElError ElDistPermutationReserveSwaps(ElDistPermutation P, ElInt maxSwaps);
+ElError ElDistPermutationSwap(ElDistPermutation P, ElInt origin, ElInt dest);
+ElError ElDistPermutationSwapSequence(ElDistPermutation P, ElConstDistPermutation PAppend, ElInt offset);
+ElError ElDistPermutationHeight(ElConstDistPermutation P, ElInt* height);
+ElError ElDistPermutationWidth(ElConstDistPermutation P, ElInt* width);
+ElError ElDistPermutationParity(ElConstDistPermutation P, bool* parity);
+ElError ElDistPermutationIsSwapSequence(ElConstDistPermutation P, bool* isSwap);
+ElError ElDistPermutationIsImplicitSwapSequence(ElConstDistPermutation P, bool* isImplicit);
+ElError ElDistPermutationImage(ElConstDistPermutation P, ElInt origin, ElInt* dest);
+ElError ElDistPermutationPreimage(ElConstDistPermutation P, ElInt dest, ElInt* origin);
+/* all Height() preimages at once (host array; no counterpart in the reference, which exposes them one at a time) */
+ElError ElDistPermutationPreimages(ElConstDistPermutation P, ElInt* preimages);
+
 ElError ElSetGemmDotBlocksize(ElInt blocksize);
 ElError ElSetStream(elb200_stream_t stream);   /* stream all work is enqueued on */
 ElError ElSynchronize(void);
@@ -201,7 +222,20 @@ ElError ElRedistStats(uint64_t out[8], bool reset);
     ElError ElCholeskySolveAfterDist_##SUF(ElUpperOrLower uplo, ElOrientation orientation,                  \
                                            ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B);                \
     ElError ElHPDSolveDist_##SUF(ElUpperOrLower uplo, ElOrientation orientation, ElConstDistMatrix_##SUF A, \
-                                 ElDistMatrix_##SUF B);
+                                 ElDistMatrix_##SUF B);                                                     \
+    /* LU (include/El/lapack_like/factor.h:465-520): without pivoting, with partial pivoting, the solves after */ \
+    ElError ElLUDist_##SUF(ElDistMatrix_##SUF A);                                                           \
+    ElError ElLUPartialPivDist_##SUF(ElDistMatrix_##SUF A, ElDistPermutation P);                            \
+    ElError ElSolveAfterLUDist_##SUF(ElOrientation orientation, ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B); \
+    ElError ElSolveAfterLUPartialPivDist_##SUF(ElOrientation orientation, ElConstDistMatrix_##SUF A,        \
+                                               ElConstDistPermutation P, ElDistMatrix_##SUF B);             \
+    /* ElLinearSolveDist (include/El/lapack_like/solve.h:26-33) */                                          \
+    ElError ElLinearSolveDist_##SUF(ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B);                       \
+    /* ElDistPermutationPermuteRows / Cols and inverses (include/El/core/Permutation.h:118-160) */          \
+    ElError ElDistPermutationPermuteRowsDist_##SUF(ElConstDistPermutation P, ElDistMatrix_##SUF A, ElInt offset); \
+    ElError ElDistPermutationInversePermuteRowsDist_##SUF(ElConstDistPermutation P, ElDistMatrix_##SUF A, ElInt offset); \
+    ElError ElDistPermutationPermuteColsDist_##SUF(ElConstDistPermutation P, ElDistMatrix_##SUF A, ElInt offset); \
+    ElError ElDistPermutationInversePermuteColsDist_##SUF(ElConstDistPermutation P, ElDistMatrix_##SUF A, ElInt offset);
 
 ELB200_DECLARE_TYPE(s, float, float)
 ELB200_DECLARE_TYPE(d, double, double)

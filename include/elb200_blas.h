@@ -200,6 +200,16 @@ int elb200_spotrf(char uplo, int64_t n, float* A, int64_t lda, int* info_dev, el
 int elb200_zpotrf(char uplo, int64_t n, elb200_c64* A, int64_t lda, int* info_dev, elb200_stream_t s);
 int elb200_cpotrf(char uplo, int64_t n, elb200_c32* A, int64_t lda, int* info_dev, elb200_stream_t s);
 
+/* LU of a tall panel with partial pivoting <- lu::Panel (src/lapack_like/factor/LU/Panel.hpp:14-55) / lu::Unb
+ * (LU/Local.hpp:44-61, pivot = 0).  A: m x n DEVICE array, m >= n, n <= 512, overwritten by unit-lower L and U;
+ * ipiv: DEVICE array of n int64, ipiv[j] = row of the panel exchanged with row j (the i?amax rule: largest |x|,
+ * |re| + |im| for complex, first occurrence); *info_dev (DEVICE int, must start at 0) = j + 1 of the first exactly
+ * zero pivot.  One cooperative kernel: row slabs per CTA, two grid barriers per column, no host round trip. */
+int elb200_dgetrf_panel(int64_t m, int64_t n, double* A, int64_t lda, int64_t* ipiv, int pivot, int* info_dev, elb200_stream_t s);
+int elb200_sgetrf_panel(int64_t m, int64_t n, float* A, int64_t lda, int64_t* ipiv, int pivot, int* info_dev, elb200_stream_t s);
+int elb200_zgetrf_panel(int64_t m, int64_t n, elb200_c64* A, int64_t lda, int64_t* ipiv, int pivot, int* info_dev, elb200_stream_t s);
+int elb200_cgetrf_panel(int64_t m, int64_t n, elb200_c32* A, int64_t lda, int64_t* ipiv, int pivot, int* info_dev, elb200_stream_t s);
+
 /* ---- FP64 tensor-pipe ceiling probe ------------------------------------ */
 /* Runs a register-resident DMMA (mma.sync m8n8k4 f64) loop on every SM and
  * returns the achieved FLOP/s through *flops_per_s: the measured FP64 tensor

@@ -170,6 +170,94 @@ int trmm(char side, char uplo, char o, char diag, int m, int n, T alpha, const T
         El::PopBlocksizeStack();
     });
 }
+// ---- section 8f rank 3: LU (src/lapack_like/factor/LU.cpp), pivoted Cholesky, CholeskyMod, LinearSolve ----
+struct BlockScope {
+    explicit BlockScope(int nb) { El::PushBlocksizeStack(nb); }
+    ~BlockScope() { El::PopBlocksizeStack(); }
+};
+// preimage[i] = the row of the input that ends up as row i of P A (DistPermutation::Preimage)
+void preimages(const El::DistPermutation& P, int n, int* out) {
+    for (int i = 0; i < n; ++i) out[i] = (int)P.Preimage(i);
+}
+template <class T>
+int lu_nopiv(int m, int n, T* A, int lda, int nb) {
+    return guarded([&] {
+        BlockScope b(nb);
+        El::DistMatrix<T> dA;
+        attach(dA, m, n, A, lda);
+        El::LU(dA);
+    });
+}
+template <class T>
+int lu_piv(int m, int n, T* A, int lda, int* preimage, int nb) {
+    return guarded([&] {
+        BlockScope b(nb);
+        El::DistMatrix<T> dA;
+        attach(dA, m, n, A, lda);
+        El::DistPermutation P(El::Grid::Default());
+        El::LU(dA, P);
+        preimages(P, m, preimage);
+    });
+}
+// factor a copy of A with partial pivoting, then lu::SolveAfter(orientation, LU, P, B)
+template <class T>
+int lu_piv_solve(char o, int n, int nrhs, const T* A, int lda, T* B, int ldb, int nb) {
+    return guarded([&] {
+        BlockScope b(nb);
+        El::DistMatrix<T> dA, dB, F;
+        lattach(dA, n, n, A, lda);
+        attach(dB, n, nrhs, B, ldb);
+        F = dA;
+        El::DistPermutation P(El::Grid::Default());
+        El::LU(F, P);
+        El::lu::SolveAfter(orient(o), F, P, dB);
+    });
+}
+template <class T>
+int linear_solve(int n, int nrhs, const T* A, int lda, T* B, int ldb, int nb) {
+    return guarded([&] {
+        BlockScope b(nb);
+        El::DistMatrix<T> dA, dB;
+        lattach(dA, n, n, A, lda);
+        attach(dB, n, nrhs, B, ldb);
+        El::LinearSolve(dA, dB);
+    });
+}
+template <class T>
+int cholesky_piv(char uplo, int n, T* A, int lda, int* preimage, int nb) {
+    return guarded([&] {
+        BlockScope b(nb);
+        El::DistMatrix<T> dA;
+        attach(dA, n, n, A, lda);
+        El::DistPermutation P(El::Grid::Default());
+        El::Cholesky(ul(uplo), dA, P);
+        preimages(P, n, preimage);
+    });
+}
+template <class T>
+int cholesky_piv_solve(char uplo, char o, int n, int nrhs, const T* A, int lda, T* B, int ldb, int nb) {
+    return guarded([&] {
+        BlockScope b(nb);
+        El::DistMatrix<T> dA, dB, F;
+        lattach(dA, n, n, A, lda);
+        attach(dB, n, nrhs, B, ldb);
+        F = dA;
+        El::DistPermutation P(El::Grid::Default());
+        El::Cholesky(ul(uplo), F, P);
+        El::cholesky::SolveAfter(ul(uplo), orient(o), F, P, dB);
+    });
+}
+// T (n x n factor, the uplo triangle) and V (n x k, overwritten) as in CholeskyMod(uplo, T, alpha, V)
+template <class T>
+int cholesky_mod(char uplo, int n, int k, T* Tf, int ldt, El::Base<T> alpha, T* V, int ldv, int nb) {
+    return guarded([&] {
+        BlockScope b(nb);
+        El::DistMatrix<T> dT, dV;
+        attach(dT, n, n, Tf, ldt);
+        attach(dV, n, k, V, ldv);
+        El::CholeskyMod(ul(uplo), dT, alpha, dV);
+    });
+}
 typedef El::Complex<double> Z;
 typedef El::Complex<float> Cf;
 }  // namespace
@@ -209,4 +297,22 @@ int elref_symm_d(char side, char uplo, int m, int n, double alpha, const double*
 int elref_symm_z(char side, char uplo, int m, int n, const double* alpha, const void* A, int lda, const void* B, int ldb, const double* beta, void* C, int ldc, int conj, int nb) { return symm<Z>(side, uplo, m, n, Z(alpha[0], alpha[1]), (const Z*)A, lda, (const Z*)B, ldb, Z(beta[0], beta[1]), (Z*)C, ldc, conj, nb); }
 int elref_trmm_d(char side, char uplo, char o, char diag, int m, int n, double alpha, const double* A, int lda, double* B, int ldb, int nb) { return trmm<double>(side, uplo, o, diag, m, n, alpha, A, lda, B, ldb, nb); }
 int elref_trmm_z(char side, char uplo, char o, char diag, int m, int n, const double* alpha, const void* A, int lda, void* B, int ldb, int nb) { return trmm<Z>(side, uplo, o, diag, m, n, Z(alpha[0], alpha[1]), (const Z*)A, lda, (Z*)B, ldb, nb); }
+int elref_lu_d(int m, int n, double* A, int lda, int nb) { return lu_nopiv<double>(m, n, A, lda, nb); }
+int elref_lu_s(int m, int n, float* A, int lda, int nb) { return lu_nopiv<float>(m, n, A, lda, nb); }
+int elref_lu_z(int m, int n, void* A, int lda, int nb) { return lu_nopiv<Z>(m, n, (Z*)A, lda, nb); }
+int elref_lu_c(int m, int n, void* A, int lda, int nb) { return lu_nopiv<Cf>(m, n, (Cf*)A, lda, nb); }
+int elref_lu_piv_d(int m, int n, double* A, int lda, int* pre, int nb) { return lu_piv<double>(m, n, A, lda, pre, nb); }
+int elref_lu_piv_s(int m, int n, float* A, int lda, int* pre, int nb) { return lu_piv<float>(m, n, A, lda, pre, nb); }
+int elref_lu_piv_z(int m, int n, void* A, int lda, int* pre, int nb) { return lu_piv<Z>(m, n, (Z*)A, lda, pre, nb); }
+int elref_lu_piv_c(int m, int n, void* A, int lda, int* pre, int nb) { return lu_piv<Cf>(m, n, (Cf*)A, lda, pre, nb); }
+int elref_lu_piv_solve_d(char o, int n, int nrhs, const double* A, int lda, double* B, int ldb, int nb) { return lu_piv_solve<double>(o, n, nrhs, A, lda, B, ldb, nb); }
+int elref_lu_piv_solve_z(char o, int n, int nrhs, const void* A, int lda, void* B, int ldb, int nb) { return lu_piv_solve<Z>(o, n, nrhs, (const Z*)A, lda, (Z*)B, ldb, nb); }
+int elref_linear_solve_d(int n, int nrhs, const double* A, int lda, double* B, int ldb, int nb) { return linear_solve<double>(n, nrhs, A, lda, B, ldb, nb); }
+int elref_linear_solve_z(int n, int nrhs, const void* A, int lda, void* B, int ldb, int nb) { return linear_solve<Z>(n, nrhs, (const Z*)A, lda, (Z*)B, ldb, nb); }
+int elref_cholesky_piv_d(char uplo, int n, double* A, int lda, int* pre, int nb) { return cholesky_piv<double>(uplo, n, A, lda, pre, nb); }
+int elref_cholesky_piv_z(char uplo, int n, void* A, int lda, int* pre, int nb) { return cholesky_piv<Z>(uplo, n, (Z*)A, lda, pre, nb); }
+int elref_cholesky_piv_solve_d(char uplo, char o, int n, int nrhs, const double* A, int lda, double* B, int ldb, int nb) { return cholesky_piv_solve<double>(uplo, o, n, nrhs, A, lda, B, ldb, nb); }
+int elref_cholesky_piv_solve_z(char uplo, char o, int n, int nrhs, const void* A, int lda, void* B, int ldb, int nb) { return cholesky_piv_solve<Z>(uplo, o, n, nrhs, (const Z*)A, lda, (Z*)B, ldb, nb); }
+int elref_cholesky_mod_d(char uplo, int n, int k, double* T, int ldt, double alpha, double* V, int ldv, int nb) { return cholesky_mod<double>(uplo, n, k, T, ldt, alpha, V, ldv, nb); }
+int elref_cholesky_mod_z(char uplo, int n, int k, void* T, int ldt, double alpha, void* V, int ldv, int nb) { return cholesky_mod<Z>(uplo, n, k, (Z*)T, ldt, alpha, (Z*)V, ldv, nb); }
 }

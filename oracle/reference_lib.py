@@ -224,3 +224,79 @@ def trmm(side, uplo, orient, diag, alpha, A, B, nb=128):
     _chk(fn(C.c_char(side.encode()), C.c_char(uplo.encode()), C.c_char(orient.encode()), C.c_char(diag.encode()),
             B.shape[0], B.shape[1], av, _p(A), A.shape[0], _p(B), B.shape[0], int(nb)))
     return B
+
+
+class RefSingular(Exception):
+    pass
+
+
+def _chk3(rc):
+    if rc == 3:
+        raise RefSingular(lib().elref_last_error().decode())
+    _chk(rc)
+
+
+# ---- LU, pivoted Cholesky, CholeskyMod, LinearSolve (reference's own code) ----
+def lu(A, nb=128):
+    """El::LU(A) without pivoting (src/lapack_like/factor/LU.cpp:21-99), in place: unit-lower L and U packed."""
+    assert A.flags.f_contiguous
+    fn = getattr(lib(), "elref_lu_" + _SUF[A.dtype])
+    _chk3(fn(A.shape[0], A.shape[1], _p(A), A.shape[0], int(nb)))
+    return A
+
+
+def lu_piv(A, nb=128):
+    """El::LU(A, P) with partial pivoting (LU.cpp:104-220).  Returns (packed LU in place, preimage vector p):
+    row i of P A is row p[i] of A, i.e. (P A) = A[p, :] = L U."""
+    assert A.flags.f_contiguous
+    pre = np.zeros(A.shape[0], dtype=np.int32)
+    fn = getattr(lib(), "elref_lu_piv_" + _SUF[A.dtype])
+    _chk3(fn(A.shape[0], A.shape[1], _p(A), A.shape[0], pre.ctypes.data_as(C.c_void_p), int(nb)))
+    return A, pre.astype(np.int64)
+
+
+def lu_piv_solve(orient, A, B, nb=128):
+    """LU(A, P) on a copy of A, then lu::SolveAfter(orientation, LU, P, B) (LU/SolveAfter.hpp): B := op(A)^{-1} B."""
+    assert B.flags.f_contiguous
+    A = _f(A, B.dtype)
+    fn = getattr(lib(), "elref_lu_piv_solve_" + _SUF[B.dtype])
+    _chk3(fn(C.c_char(orient.encode()), A.shape[0], B.shape[1], _p(A), A.shape[0], _p(B), B.shape[0], int(nb)))
+    return B
+
+
+def linear_solve(A, B, nb=128):
+    """El::LinearSolve(A, B) (src/lapack_like/solve/Linear.cpp: RowEchelon + back substitution)."""
+    assert B.flags.f_contiguous
+    A = _f(A, B.dtype)
+    fn = getattr(lib(), "elref_linear_solve_" + _SUF[B.dtype])
+    _chk3(fn(A.shape[0], B.shape[1], _p(A), A.shape[0], _p(B), B.shape[0], int(nb)))
+    return B
+
+
+def cholesky_piv(uplo, A, nb=128):
+    """El::Cholesky(uplo, A, P) with diagonal pivoting (Cholesky/PivotedLowerVariant3.hpp, PivotedUpperVariant3.hpp).
+    Returns (factor in the uplo triangle, preimage vector p): A[p][:, p] = L L^H (or U^H U)."""
+    assert A.flags.f_contiguous
+    pre = np.zeros(A.shape[0], dtype=np.int32)
+    fn = getattr(lib(), "elref_cholesky_piv_" + _SUF[A.dtype])
+    _chk(fn(C.c_char(uplo.encode()), A.shape[0], _p(A), A.shape[0], pre.ctypes.data_as(C.c_void_p), int(nb)))
+    return A, pre.astype(np.int64)
+
+
+def cholesky_piv_solve(uplo, orient, A, B, nb=128):
+    assert B.flags.f_contiguous
+    A = _f(A, B.dtype)
+    fn = getattr(lib(), "elref_cholesky_piv_solve_" + _SUF[B.dtype])
+    _chk(fn(C.c_char(uplo.encode()), C.c_char(orient.encode()), A.shape[0], B.shape[1], _p(A), A.shape[0], _p(B),
+            B.shape[0], int(nb)))
+    return B
+
+
+def cholesky_mod(uplo, T, alpha, V, nb=128):
+    """El::CholeskyMod(uplo, T, alpha, V) (Cholesky/LowerMod.hpp, UpperMod.hpp): the factor of T T^H + alpha V V^H
+    (LOWER) or T^H T + alpha V V^H (UPPER) overwrites T; V is overwritten with workspace."""
+    assert T.flags.f_contiguous and V.flags.f_contiguous
+    fn = getattr(lib(), "elref_cholesky_mod_" + _SUF[T.dtype])
+    _chk(fn(C.c_char(uplo.encode()), T.shape[0], V.shape[1], _p(T), T.shape[0],
+            C.c_double(float(alpha)), _p(V), V.shape[0], int(nb)))
+    return T

@@ -223,6 +223,51 @@ def main():
     if not np.linalg.norm(dC.ToGlobal() - O.herk("L", "N", -1.0, A, 1.0, C0.copy())) <= 1e-11:
         fails.append("herk")
 
+    # 5. LU with partial pivoting (the panel is replicated, the interchanges all-gather inside the process column),
+    #    lu::SolveAfter, LinearSolve and the permutation applied to distributed matrices; against the numpy
+    #    restatement at the same Blocksize() (pinned to the reference on the CPU: tests/test_oracle_cpu.py)
+    for dt, (m, n, nb) in ((np.float64, (150, 150, 32)), (np.complex128, (130, 170, 32)), (np.float64, (170, 90, 48))):
+        A = O.fill(0, m, n, 31, dtype=dt)
+        F = A.copy(order="F")
+        pref = O.lu(F, nb)
+        dA = dm(A)
+        P = El.DistPermutation(g)
+        El.PushBlocksizeStack(nb)
+        El.LU(dA, P)
+        El.PopBlocksizeStack()
+        p = P.Preimages()
+        if not np.array_equal(p, pref):
+            fails.append(f"lu pivots {np.dtype(dt).name} {m}x{n}")
+        elif not np.linalg.norm(dA.ToGlobal() - F) <= 50 * max(m, n) * np.finfo(np.float64).eps * np.linalg.norm(A):
+            fails.append(f"lu factors {np.dtype(dt).name} {m}x{n}")
+        for dist_ in ((0, 2), (3, 5), (5, 4), (2, 0)):
+            X0 = O.fill(0, m, 23, 32, dtype=dt)
+            dX = dm(X0, dist_)
+            P.PermuteRows(dX)
+            ok = np.array_equal(dX.ToGlobal(), X0[pref, :])
+            P.InversePermuteRows(dX)
+            if not (ok and np.array_equal(dX.ToGlobal(), X0)):
+                fails.append(f"permute rows {dist_}")
+    n, nb = 140, 32
+    A = O.fill(0, n, n, 33)
+    B0 = O.fill(0, n, 40, 34)
+    dF, P = dm(A), El.DistPermutation(g)
+    El.PushBlocksizeStack(nb)
+    El.LU(dF, P)
+    for o in "NT":
+        dB = dm(B0)
+        El.LUSolveAfter(ORI[o], dF, dB, P)
+        X = dB.ToGlobal()
+        opA = A if o == "N" else A.T
+        if not np.linalg.norm(opA @ X - B0) <= 10 * n * np.finfo(np.float64).eps * np.linalg.norm(A) * np.linalg.norm(X):
+            fails.append(f"lu solve {o}")
+    dB = dm(B0)
+    El.LinearSolve(dm(A), dB)
+    X = dB.ToGlobal()
+    El.PopBlocksizeStack()
+    if not np.linalg.norm(A @ X - B0) <= 10 * n * np.finfo(np.float64).eps * np.linalg.norm(A) * np.linalg.norm(X):
+        fails.append("linear solve")
+
     bad = torch.tensor([len(fails)], device="cuda")
     dist.all_reduce(bad)
     if fails:

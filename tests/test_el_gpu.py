@@ -436,6 +436,12 @@ def test_views_and_blocksize_stack(El):
     El.PushBlocksizeStack(77); assert El.Blocksize() == 77
     El.SetBlocksize(55); assert El.Blocksize() == 55
     El.PopBlocksizeStack(); assert El.Blocksize() == b0
+    # shrinking keeps the leading dimension and the leading block (Matrix/impl.hpp:698-717: "simply shrink our view")
+    ld = A.LDim()
+    A.Resize(25, 20)
+    assert A.LDim() == ld and np.array_equal(A.ToGlobal(), G[:25, :20])
+    A.Resize(41, 20)   # growing reallocates: contents undefined, size right
+    assert (A.Height(), A.Width()) == (41, 20) and A.LDim() >= 41
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.complex128, np.float32])
