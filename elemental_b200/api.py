@@ -628,6 +628,25 @@ def LUSolveAfter(orient, A: DistMatrix, B: DistMatrix, P: DistPermutation | None
         _check(_same(A, B)._fn("ElSolveAfterLUPartialPivDist")(orient, A._h, P._h, B._h), "ElSolveAfterLUPartialPivDist")
 
 
+def CholeskyPiv(uplo, A: DistMatrix, P: DistPermutation):
+    """El::Cholesky(uplo, A, P) (src/lapack_like/factor/Cholesky.cpp:112-121): diagonally pivoted, P A P^T = L L^H."""
+    _sync_stream()
+    _check(A._fn("ElCholeskyPivDist")(uplo, A._h, P._h), "ElCholeskyPivDist")
+
+
+def CholeskyPivSolveAfter(uplo, orient, A: DistMatrix, P: DistPermutation, B: DistMatrix):
+    """cholesky::SolveAfter(uplo, orientation, A, P, B) (Cholesky/SolveAfter.hpp:108-141)."""
+    _sync_stream()
+    _check(_same(A, B)._fn("ElSolveAfterCholeskyPivDist")(uplo, orient, A._h, P._h, B._h), "ElSolveAfterCholeskyPivDist")
+
+
+def CholeskyMod(uplo, T: DistMatrix, alpha: float, V: DistMatrix):
+    """El::CholeskyMod(uplo, T, alpha, V) (src/lapack_like/factor/Cholesky.cpp:143-173): T becomes the factor of
+    T T^H + alpha V V^H (LOWER) / T^H T + alpha V V^H (UPPER); V is overwritten with workspace."""
+    _sync_stream()
+    _check(_same(T, V)._fn("ElCholeskyModDist")(uplo, T._h, _real(T.dtype, alpha), V._h), "ElCholeskyModDist")
+
+
 def LinearSolve(A: DistMatrix, B: DistMatrix):
     """El::LinearSolve(A, B) (src/lapack_like/solve/Linear.cpp): B := inv(A) B, A unchanged."""
     _sync_stream()

@@ -349,6 +349,16 @@ ElError ElRedistStats(uint64_t out[8], bool reset) {
                                                ElDistMatrix_##SUF B) {                                             \
         return Try([&] { lu::SolveAfter(O(o), *CM_##SUF(A), *CPM(P), *M_##SUF(B)); });                             \
     }                                                                                                              \
+    ElError ElCholeskyPivDist_##SUF(ElUpperOrLower uplo, ElDistMatrix_##SUF A, ElDistPermutation P) {              \
+        return Try([&] { Cholesky(UL(uplo), *M_##SUF(A), *PM(P)); });                                              \
+    }                                                                                                              \
+    ElError ElSolveAfterCholeskyPivDist_##SUF(ElUpperOrLower uplo, ElOrientation o, ElConstDistMatrix_##SUF A,     \
+                                              ElConstDistPermutation P, ElDistMatrix_##SUF B) {                    \
+        return Try([&] { cholesky::SolveAfter(UL(uplo), O(o), *CM_##SUF(A), *CPM(P), *M_##SUF(B)); });             \
+    }                                                                                                              \
+    ElError ElCholeskyModDist_##SUF(ElUpperOrLower uplo, ElDistMatrix_##SUF T_, REAL alpha, ElDistMatrix_##SUF V) { \
+        return Try([&] { CholeskyMod(UL(uplo), *M_##SUF(T_), alpha, *M_##SUF(V)); });                              \
+    }                                                                                                              \
     ElError ElLinearSolveDist_##SUF(ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B) {                             \
         return Try([&] { LinearSolve(*CM_##SUF(A), *M_##SUF(B)); });                                               \
     }                                                                                                              \

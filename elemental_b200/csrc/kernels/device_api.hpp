@@ -66,6 +66,28 @@ void permute_device(bool rowwise, i64 mloc, i64 nloc, const i64* perm, int shift
 // origins[at + j] = offset + j, dests[at + j] = offset + ipiv[j]
 void append_swaps_device(i64* origins, i64* dests, i64 at, const i64* ipiv, int count, i64 offset, cudaStream_t s);
 
+// rank-w update (downdate) of the M x nb panel L of a Cholesky factor whose first row is the diagonal row of its
+// first column, with V (M x w, same rows) carrying the state between panels (cholmod.cu); *info_dev := 1 when a
+// downdate would make the matrix indefinite
+template <class T>
+void cholmod_panel_device(bool downdate, i64 M, i64 nb, T* L, i64 ldl, T* V, i64 ldv, i64 w, int* info_dev, cudaStream_t s);
+
+// diagonally pivoted Cholesky (cholpiv.cu): replicated panel state, plain local kernels
+template <class T>
+void diag_extract_device(i64 mloc, i64 nloc, const T* A, i64 lda, int colShift, int colStride, int rowShift, int rowStride,
+                         double* d, cudaStream_t s);                       // d[i] = Re A(i,i) for the owned diagonal entries
+void argmax_abs_device(const double* d, i64 lo, i64 hi, i64* out, cudaStream_t s);   // first index of max |d[lo:hi)|
+template <class T>
+void pivot_swap_device(int k, i64 f, double* d, T* X, i64 ldx, i64* pos, i64* ipiv, cudaStream_t s);
+template <class T>
+void pivot_column_device(i64 M, int k, const T* h, const i64* pos, T* X, i64 ldx, double* d, int* info, i64 col, cudaStream_t s);
+template <class T>
+void pack_cols_device(int S, const i64* slotCol, const int* srcSlot, const T* A, i64 lda, i64 mloc, int align, int stride,
+                      int rank, int shift, T* buf, cudaStream_t s);
+template <class T>
+void unpack_cols_device(int S, const i64* slotCol, const int* srcSlot, T* A, i64 lda, i64 mloc, int align, int stride,
+                        int rank, int shift, const T* all, i64 perRank, cudaStream_t s);
+
 // dst (op)= alpha*op(src) on one strided block (level1.cu)
 template <class T>
 void lattice_copy_device(const T* src, T* dst, i64 nrows, i64 ncols, i64 s_off, i64 s_rs, i64 s_cs,

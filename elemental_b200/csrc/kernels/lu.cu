@@ -13,6 +13,7 @@
 // memory, two grid barriers per column, no host round trip -- the pivots stay on the device and feed the
 // interchange kernels directly.  The pivot rule is the reference's (i?amax: largest |x|, |re| + |im| for complex,
 // first occurrence), so the permutation is the one the reference (and LAPACK getrf) produces.
+#include "coop.cuh"
 #include "device_api.hpp"
 #include "elb200_blas.h"
 
@@ -44,31 +45,7 @@ template <class R> __device__ inline cplx<R> recip_c(cplx<R> x) {
 template <> __device__ inline c32_t recip<c32_t>(c32_t x) { return recip_c(x); }
 template <> __device__ inline c64_t recip<c64_t>(c64_t x) { return recip_c(x); }
 
-template <class T> __device__ inline T ldcg(const T* p) { return __ldcg(p); }
-template <> __device__ inline c32_t ldcg<c32_t>(const c32_t* p) {
-    const float2 v = __ldcg(reinterpret_cast<const float2*>(p));
-    return mk(v.x, v.y);
-}
-template <> __device__ inline c64_t ldcg<c64_t>(const c64_t* p) {
-    const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
-    return mk(v.x, v.y);
-}
-
 __device__ inline bool better(double v, long long i, double bv, long long bi) { return v > bv || (v == bv && i < bi); }
-
-// all CTAs of the (cooperatively launched, hence co-resident) grid meet; `bar` only grows
-__device__ inline void grid_barrier(unsigned* bar, unsigned nblk, unsigned& epoch) {
-    ++epoch;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
-        const unsigned target = epoch * nblk;
-        while (*(volatile unsigned*)bar < target) {}
-        __threadfence();
-    }
-    __syncthreads();
-}
 
 __device__ inline void block_best(double& v, long long& i, Cand* red) {
     for (int o = 16; o > 0; o >>= 1) {

@@ -89,4 +89,19 @@ void SolveAfter(Orientation orientation, const AbstractDistMatrix<F>& A, const D
 template <typename F> void LinearSolve(const Matrix<F>& A, Matrix<F>& B);
 template <typename F> void LinearSolve(const AbstractDistMatrix<F>& A, AbstractDistMatrix<F>& B, bool scalapack = false);
 
+// ---- the rest of the Cholesky family (include/El/lapack_like/factor.hpp:36-90) ----
+// Diagonally pivoted factorisation P A P^T = L L^H (LOWER) / U^H U (UPPER) of a Hermitian positive (semi)definite
+// matrix, pivoting on the largest remaining diagonal entry; only the uplo triangle of A is read and written.
+template <typename F> void Cholesky(UpperOrLower uplo, Matrix<F>& A, Permutation& P);
+template <typename F> void Cholesky(UpperOrLower uplo, AbstractDistMatrix<F>& A, DistPermutation& P);
+namespace cholesky {
+template <typename F>
+void SolveAfter(UpperOrLower uplo, Orientation orientation, const AbstractDistMatrix<F>& A, const DistPermutation& P,
+                AbstractDistMatrix<F>& B);
+}  // namespace cholesky
+// T := factor of T T^H + alpha V V^H (LOWER) / T^H T + alpha V V^H (UPPER); V (n x w) is overwritten with workspace.
+// A downdate that would make the matrix indefinite throws std::logic_error, as the reference's reflector does.
+template <typename F> void CholeskyMod(UpperOrLower uplo, Matrix<F>& T, Base<F> alpha, Matrix<F>& V);
+template <typename F> void CholeskyMod(UpperOrLower uplo, AbstractDistMatrix<F>& T, Base<F> alpha, AbstractDistMatrix<F>& V);
+
 }  // namespace El

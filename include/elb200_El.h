@@ -229,6 +229,12 @@ ElError ElRedistStats(uint64_t out[8], bool reset);
     ElError ElSolveAfterLUDist_##SUF(ElOrientation orientation, ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B); \
     ElError ElSolveAfterLUPartialPivDist_##SUF(ElOrientation orientation, ElConstDistMatrix_##SUF A,        \
                                                ElConstDistPermutation P, ElDistMatrix_##SUF B);             \
+    /* ElCholeskyPivDist / ElSolveAfterCholeskyPivDist (include/El/lapack_like/factor.h:80-124): P A P^T = L L^H */ \
+    ElError ElCholeskyPivDist_##SUF(ElUpperOrLower uplo, ElDistMatrix_##SUF A, ElDistPermutation P);        \
+    ElError ElSolveAfterCholeskyPivDist_##SUF(ElUpperOrLower uplo, ElOrientation orientation,               \
+                                              ElConstDistMatrix_##SUF A, ElConstDistPermutation P, ElDistMatrix_##SUF B); \
+    /* ElCholeskyModDist (include/El/lapack_like/factor.h:127-145): T T^H + alpha V V^H = That That^H */    \
+    ElError ElCholeskyModDist_##SUF(ElUpperOrLower uplo, ElDistMatrix_##SUF T, REAL alpha, ElDistMatrix_##SUF V); \
     /* ElLinearSolveDist (include/El/lapack_like/solve.h:26-33) */                                          \
     ElError ElLinearSolveDist_##SUF(ElConstDistMatrix_##SUF A, ElDistMatrix_##SUF B);                       \
     /* ElDistPermutationPermuteRows / Cols and inverses (include/El/core/Permutation.h:118-160) */          \

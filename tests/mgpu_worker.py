@@ -268,6 +268,43 @@ def main():
     if not np.linalg.norm(A @ X - B0) <= 10 * n * np.finfo(np.float64).eps * np.linalg.norm(A) * np.linalg.norm(X):
         fails.append("linear solve")
 
+    # 6. CholeskyMod and the diagonally pivoted Cholesky (replicated panel state, slot interchanges in both
+    #    communicators) against the numpy restatements
+    n, nb = 150, 32
+    Gm = O.fill(0, n, n, 41)
+    S = Gm @ Gm.T / n + 0.05 * np.eye(n)
+    S = np.asfortranarray((S + S.T) / 2)
+    L0 = np.linalg.cholesky(S)
+    El.PushBlocksizeStack(nb)
+    for uplo in "LU":
+        T0 = np.asfortranarray(L0 if uplo == "L" else L0.T)
+        for w, alpha in ((7, 0.4), (3, -0.01)):
+            V = O.fill(0, n, w, 42 + w)
+            dT = dm(T0)
+            El.CholeskyMod(0 if uplo == "L" else 1, dT, alpha, dm(V))
+            got = dT.ToGlobal()
+            Lg = np.tril(got) if uplo == "L" else np.triu(got).T
+            target = S + alpha * (V @ V.T)
+            if not np.linalg.norm(Lg @ Lg.T - target) <= 10 * n * np.finfo(np.float64).eps * np.linalg.norm(target):
+                fails.append(f"cholesky mod {uplo} {alpha}")
+        dA, P = dm(S), El.DistPermutation(g)
+        El.CholeskyPiv(0 if uplo == "L" else 1, dA, P)
+        got, p = dA.ToGlobal(), P.Preimages()
+        Fo = S.copy(order="F")
+        po = O.cholesky_pivoted(uplo, Fo)
+        Lg = np.tril(got) if uplo == "L" else np.triu(got).T
+        if not np.array_equal(p, po):
+            fails.append(f"pivoted cholesky pivots {uplo}")
+        if not np.linalg.norm(S[np.ix_(p, p)] - Lg @ Lg.T) <= 10 * n * np.finfo(np.float64).eps * np.linalg.norm(S):
+            fails.append(f"pivoted cholesky {uplo}")
+        B0 = O.fill(0, n, 11, 44)
+        dB = dm(B0)
+        El.CholeskyPivSolveAfter(0 if uplo == "L" else 1, 0, dA, P, dB)
+        X = dB.ToGlobal()
+        if not np.linalg.norm(S @ X - B0) <= 1e3 * n * np.finfo(np.float64).eps * np.linalg.norm(S) * np.linalg.norm(X):
+            fails.append(f"pivoted cholesky solve {uplo}")
+    El.PopBlocksizeStack()
+
     bad = torch.tensor([len(fails)], device="cuda")
     dist.all_reduce(bad)
     if fails:

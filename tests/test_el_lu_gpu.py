@@ -275,3 +275,99 @@ def test_permutation_object_against_numpy(El, dt):
         P.Swap(0, sz)
     with pytest.raises(El.Elb200Error):
         P.PermuteRows(_dm(El, A), m - sz + 1)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128, np.float32])
+def test_cholesky_mod_matches_reference(El, dt):
+    """El::CholeskyMod (Cholesky/LowerMod.hpp, UpperMod.hpp): update (alpha > 0) and downdate (alpha < 0) of a factor
+    by a rank-w term, against the reference itself when built (else the unique factor of the modified matrix), for
+    both triangles, several widths, a Blocksize() smaller than n, and a [VC,*] V."""
+    n, nb = 230, 64
+    G = O.fill(0, n, n, 61, dtype=dt)
+    S = G @ G.conj().T / n + np.eye(n, dtype=dt)
+    S = ((S + S.conj().T) / 2).astype(dt)
+    L0 = np.linalg.cholesky(S.astype(np.complex128 if np.dtype(dt).kind == "c" else np.float64)).astype(dt)
+    eps = _eps(dt)
+    El.PushBlocksizeStack(nb)
+    try:
+        for uplo in "LU":
+            T0 = np.asfortranarray(L0 if uplo == "L" else L0.conj().T)
+            # junk in the other triangle must survive
+            junk = O.fill(0, n, n, 62, dtype=dt)
+            T0 = np.asfortranarray(T0 + (np.triu(junk, 1) if uplo == "L" else np.tril(junk, -1)))
+            for w, alpha in ((1, 0.7), (5, 0.5), (40, 0.3), (3, -0.05), (17, -0.01)):
+                V = np.asfortranarray(O.fill(0, n, w, 63 + w, dtype=dt))
+                dT = _dm(El, T0)
+                dV = _dm(El, V, (El.VC, El.STAR) if w == 5 else (El.MC, El.MR))
+                El.CholeskyMod(0 if uplo == "L" else 1, dT, alpha, dV)
+                got = dT.ToGlobal()
+                tri = np.tril(got) if uplo == "L" else np.triu(got)
+                other = np.triu(got, 1) if uplo == "L" else np.tril(got, -1)
+                assert np.array_equal(other, np.triu(T0, 1) if uplo == "L" else np.tril(T0, -1)), (uplo, w)
+                Lg = tri if uplo == "L" else tri.conj().T
+                target = S + alpha * (V @ V.conj().T)
+                res = np.linalg.norm(Lg @ Lg.conj().T - target) / (n * eps * np.linalg.norm(target))
+                assert res <= 10.0, (dt, uplo, w, alpha, res)
+                assert np.all(np.diag(Lg).real > 0) and np.all(np.abs(np.diag(Lg).imag) == 0)
+                if R.available() and dt != np.float32:
+                    ref = R.cholesky_mod(uplo, T0.copy(order="F"), alpha, V.copy(order="F"), nb=nb)
+                    rtri = np.tril(ref) if uplo == "L" else np.triu(ref)
+                    assert np.linalg.norm(tri - rtri) <= 1e3 * n * eps * np.linalg.norm(rtri), (dt, uplo, w, alpha)
+        # a downdate that leaves the matrix indefinite raises, as the reference's hyperbolic reflector does
+        V = np.asfortranarray(10.0 * O.fill(0, n, 2, 64, dtype=dt))
+        with pytest.raises(El.LogicError):
+            El.CholeskyMod(0, _dm(El, np.asfortranarray(L0)), -1.0, _dm(El, V))
+    finally:
+        El.PopBlocksizeStack()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128, np.float32])
+def test_pivoted_cholesky(El, dt):
+    """El::Cholesky(uplo, A, P): P A P^T = L L^H with the largest remaining diagonal entry as pivot.  The reference's
+    own pivot order depends on stale memory (see tests/test_oracle_cpu.py), so the oracle is the numpy restatement of
+    the algorithm as stated (oracle.cholesky_pivoted: identical permutation, factor to rounding) plus the identity,
+    the ordered diagonal, the untouched other triangle and the solve after."""
+    n, nb = 210, 48
+    G = O.fill(0, n, n, 71, dtype=dt)
+    S = G @ G.conj().T / n + 0.05 * np.eye(n, dtype=dt)
+    S = np.asfortranarray(((S + S.conj().T) / 2).astype(dt))
+    eps = _eps(dt)
+    junk = O.fill(0, n, n, 72, dtype=dt)
+    B = O.fill(0, n, 9, 73, dtype=dt)
+    El.PushBlocksizeStack(nb)
+    try:
+        for uplo in "LU":
+            A0 = np.asfortranarray((np.tril(S) + np.triu(junk, 1)) if uplo == "L" else (np.triu(S) + np.tril(junk, -1)))
+            for dist in ((El.MC, El.MR), (El.VC, El.STAR)):
+                dA = _dm(El, A0, dist)
+                P = El.DistPermutation()
+                El.CholeskyPiv(0 if uplo == "L" else 1, dA, P)
+                got, p = dA.ToGlobal(), P.Preimages()
+                Fo = A0.copy(order="F")
+                po = O.cholesky_pivoted(uplo, Fo)
+                Lg = np.tril(got) if uplo == "L" else np.triu(got).conj().T
+                other = np.triu(got, 1) if uplo == "L" else np.tril(got, -1)
+                assert np.array_equal(other, np.triu(A0, 1) if uplo == "L" else np.tril(A0, -1)), (uplo, dist)
+                assert sorted(p.tolist()) == list(range(n))
+                res = np.linalg.norm(S[np.ix_(p, p)] - Lg @ Lg.conj().T) / (n * eps * np.linalg.norm(S))
+                assert res <= 10.0, (dt, uplo, res)
+                dg = np.diag(Lg).real
+                assert np.all(np.diff(dg) <= 50 * n * eps * dg[0]), (dt, uplo)      # pivoting orders the diagonal
+                if dt != np.float32:
+                    assert np.array_equal(p, po), (dt, uplo)
+                    Lo = np.tril(Fo) if uplo == "L" else np.triu(Fo).conj().T
+                    assert np.linalg.norm(Lg - Lo) <= 1e3 * n * eps * np.linalg.norm(Lo), (dt, uplo)
+                for o in "NT":
+                    dB = _dm(El, B)
+                    El.CholeskyPivSolveAfter(0 if uplo == "L" else 1, ORI[o], dA, P, dB)
+                    X = dB.ToGlobal()
+                    opS = S if o == "N" else S.T
+                    assert np.linalg.norm(opS @ X - B) <= 1e3 * n * eps * np.linalg.norm(S) * np.linalg.norm(X), (dt, uplo, o)
+        # semidefinite input of rank 40: pivoting pushes the zero pivots to the end, where the factorisation stops
+        Glow = O.fill(0, n, 40, 74, dtype=dt)
+        Z = np.asfortranarray((Glow @ Glow.conj().T).astype(dt))
+        Z[np.diag_indices(n)] = Z[np.diag_indices(n)].real
+        with pytest.raises(El.NonHPDMatrixException):
+            El.CholeskyPiv(0, _dm(El, Z - 1e-3 * np.eye(n, dtype=dt)), El.DistPermutation())
+    finally:
+        El.PopBlocksizeStack()
