@@ -278,7 +278,7 @@ def main():
     El.PushBlocksizeStack(nb)
     for uplo in "LU":
         T0 = np.asfortranarray(L0 if uplo == "L" else L0.T)
-        for w, alpha in ((7, 0.4), (3, -0.01)):
+        for w, alpha in ((7, 0.4), (3, -0.0003)):
             V = O.fill(0, n, w, 42 + w)
             dT = dm(T0)
             El.CholeskyMod(0 if uplo == "L" else 1, dT, alpha, dm(V))
