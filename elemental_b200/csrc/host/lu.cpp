@@ -291,34 +291,56 @@ void LUBlocked(AbstractDistMatrix<F>& A, DistPermutation* P, dev::DeviceFlag& in
     i64* ipiv = P ? (i64*)elb200::scratch_alloc(sizeof(i64) * (size_t)bsize, s) : nullptr;
     std::unique_ptr<PanelSwapper<F>> swapper;
     if (P) swapper.reset(new PanelSwapper<F>(bsize));
+    dev::PhaseTimer tm;   // ELB200_TRACE=1: serialised per-phase device times
     for (Int k = 0; k < minDim; k += bsize) {
         const Int nb = std::min(bsize, minDim - k);
         auto AB1 = View(A, k, k, m - k, nb);
+        tm.Begin(s);
         Copy(C(AB1), panel);
+        tm.End(s, "panel -> [*,*]");
+        tm.Begin(s);
         elb200::getrf_panel_device<D>(m - k, nb, dev::ptr(panel.Buffer()), panel.LDim(), ipiv, P != nullptr, info.dev_, k, s);
+        tm.End(s, "getrf(panel)");
         if (P) {
+            tm.Begin(s);
             P->AppendDeviceSwaps(ipiv, nb, k);
             swapper->Run(A, k, nb, ipiv);   // all columns: the panel's own are overwritten next
+            tm.End(s, "row interchanges");
         }
+        tm.Begin(s);
         Copy(C(panel), AB1);
+        tm.End(s, "panel <- [*,*]");
         if (k + nb < n) {
             auto A12 = View(A, k, k + nb, nb, n - k - nb);
             auto A11 = LockedView(C(panel), 0, 0, nb, nb);
             A12_STAR_VR.AlignWith(A12);
+            tm.Begin(s);
             Copy(C(A12), A12_STAR_VR);
+            tm.End(s, "A12 -> [*,VR]");
+            tm.Begin(s);
             LocalTrsm(LEFT, LOWER, NORMAL, UNIT, F(1), C(A11), A12_STAR_VR);
+            tm.End(s, "trsm(A12)");
             A12_STAR_MR.AlignWith(A12);
+            tm.Begin(s);
             Copy(C(A12_STAR_VR), A12_STAR_MR);
+            tm.End(s, "A12 [*,VR] -> [*,MR]");
             if (k + nb < m) {
                 auto A22 = View(A, k + nb, k + nb, m - k - nb, n - k - nb);
                 auto L21 = LockedView(C(panel), nb, 0, m - k - nb, nb);
                 A21_MC_STAR.AlignWith(A22);
+                tm.Begin(s);
                 Copy(C(L21), A21_MC_STAR);
+                tm.End(s, "L21 [*,*] -> [MC,*]");
+                tm.Begin(s);
                 LocalGemm(NORMAL, NORMAL, F(-1), C(A21_MC_STAR), C(A12_STAR_MR), F(1), A22);
+                tm.End(s, "trailing update (gemm)");
             }
+            tm.Begin(s);
             Copy(C(A12_STAR_MR), A12);
+            tm.End(s, "A12 <- [*,MR]");
         }
     }
+    tm.Report("LU");
     if (ipiv) elb200::scratch_free(ipiv, s);
 }
 

@@ -13,6 +13,8 @@
 // memory, two grid barriers per column, no host round trip -- the pivots stay on the device and feed the
 // interchange kernels directly.  The pivot rule is the reference's (i?amax: largest |x|, |re| + |im| for complex,
 // first occurrence), so the permutation is the one the reference (and LAPACK getrf) produces.
+#include <cstdlib>
+
 #include "coop.cuh"
 #include "device_api.hpp"
 #include "elb200_blas.h"
@@ -171,6 +173,197 @@ __global__ void __launch_bounds__(LU_THREADS) lu_panel_kernel(i64 M, int n, T* A
     }
 }
 
+// ---- second generation: IMPLICIT interchanges ------------------------------------------------------------------
+// Rows do not move while the panel is factored: the pivot row of column j is read where it lies and marked done, the
+// others are eliminated in place.  Nothing is overwritten that another CTA still reads, so ONE grid barrier per column
+// suffices (the first generation needed a second one between reading and exchanging the two rows).  Every CTA keeps the
+// same small bookkeeping (which physical row sits at positions 0 .. n-1, where each of the first n physical rows has
+// been displaced to), which gives (i) LAPACK's tie-break -- first occurrence in the CURRENT order, not the physical
+// one -- and (ii) ipiv[j] directly.  At the end the <= 2 n rows whose position differs from their physical index are
+// staged and written to their places.
+struct Cand2 {
+    double val;
+    long long key;   // current position of the row (tie-break)
+    long long row;   // physical row
+};
+__device__ inline bool better2(double v, long long k, double bv, long long bk) { return v > bv || (v == bv && k < bk); }
+
+template <class T, bool PIVOT>
+__global__ void __launch_bounds__(LU_THREADS) lu_panel_ip_kernel(i64 M, int n, T* A, i64 lda, i64* ipiv, int* info, i64 col0,
+                                                                 unsigned* bar, Cand2* cand, i64 rows, unsigned char* done,
+                                                                 T* stage) {
+    __shared__ T u[LU_MAX_N];
+    __shared__ double rv[LU_THREADS / 32];
+    __shared__ long long rk[LU_THREADS / 32], rr[LU_THREADS / 32];
+    __shared__ long long rowAt[LU_MAX_N];   // physical row at position j < n
+    __shared__ long long posTop[LU_MAX_N];  // current position of physical row r < n
+    __shared__ long long sPiv;
+    __shared__ int sSingular;
+    const unsigned nblk = gridDim.x;
+    unsigned epoch = 0;
+    const i64 r0 = (i64)blockIdx.x * rows, r1 = (r0 + rows < M) ? r0 + rows : M;
+    const int t = threadIdx.x;
+    const long long BIG = 0x7fffffffffffffffLL;
+    for (int c = t; c < n; c += LU_THREADS) { rowAt[c] = c; posTop[c] = c; }
+    __syncthreads();
+
+    auto block_reduce = [&](double& v, long long& k, long long& r) {
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, v, o);
+            const long long ok = __shfl_down_sync(0xffffffffu, k, o);
+            const long long orr = __shfl_down_sync(0xffffffffu, r, o);
+            if (better2(ov, ok, v, k)) { v = ov; k = ok; r = orr; }
+        }
+        const int w = t >> 5, l = t & 31;
+        if (l == 0) { rv[w] = v; rk[w] = k; rr[w] = r; }
+        __syncthreads();
+        if (w == 0) {
+            v = l < (LU_THREADS >> 5) ? rv[l] : -1.0;
+            k = l < (LU_THREADS >> 5) ? rk[l] : BIG;
+            r = l < (LU_THREADS >> 5) ? rr[l] : 0;
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, v, o);
+                const long long ok = __shfl_down_sync(0xffffffffu, k, o);
+                const long long orr = __shfl_down_sync(0xffffffffu, r, o);
+                if (better2(ov, ok, v, k)) { v = ov; k = ok; r = orr; }
+            }
+        }
+        __syncthreads();
+    };
+
+    if (PIVOT) {   // candidates of column 0: every row, positions = physical indices
+        double bv = -1.0;
+        long long bk = BIG, br = 0;
+        for (i64 i = r0 + t; i < r1; i += LU_THREADS) {
+            const double v = abs1(A[i]);
+            if (better2(v, i, bv, bk)) { bv = v; bk = i; br = i; }
+        }
+        block_reduce(bv, bk, br);
+        if (t == 0) { cand[blockIdx.x].val = bv; cand[blockIdx.x].key = bk; cand[blockIdx.x].row = br; }
+    }
+    for (int j = 0; j < n; ++j) {
+        grid_barrier(bar, nblk, epoch);   // every row carries the updates of columns < j; candidates of column j are out
+        if (t < 32) {
+            double bv = -1.0;
+            long long bk = BIG, br = 0;
+            if (PIVOT) {
+                for (unsigned b = t; b < nblk; b += 32) {
+                    const double v = __ldcg(&cand[b].val);
+                    const long long k = __ldcg(&cand[b].key), r = __ldcg(&cand[b].row);
+                    if (better2(v, k, bv, bk)) { bv = v; bk = k; br = r; }
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+                    const long long ok = __shfl_down_sync(0xffffffffu, bk, o);
+                    const long long orr = __shfl_down_sync(0xffffffffu, br, o);
+                    if (better2(ov, ok, bv, bk)) { bv = ov; bk = ok; br = orr; }
+                }
+            }
+            if (t == 0) {
+                long long p, q;
+                int singular;
+                if (PIVOT) {
+                    singular = !(bv > 0.0);
+                    p = singular ? rowAt[j] : br;     // nothing to choose from: LAPACK keeps the row at position j
+                    q = singular ? (long long)j : bk;
+                    const long long r = rowAt[j];     // always one of the first n physical rows
+                    if (q != j) {
+                        if (q < n) rowAt[q] = r;
+                        posTop[r] = q;
+                    }
+                    rowAt[j] = p;
+                    if (p < n) posTop[p] = j;
+                } else {
+                    p = j; q = j;
+                    singular = scalar_traits<T>::is_zero(ldcg(&A[j + (i64)j * lda]));
+                }
+                sPiv = p;
+                sSingular = singular;
+                if (p >= r0 && p < r1) done[p] = 1;
+                if (blockIdx.x == 0) {
+                    if (ipiv) ipiv[j] = q;
+                    if (singular) atomicCAS(info, 0, (int)(col0 + j + 1));
+                }
+            }
+        }
+        __syncthreads();
+        const i64 piv = sPiv;
+        const bool singular = sSingular != 0;
+        for (int c = j + t; c < n; c += LU_THREADS) u[c] = ldcg(&A[piv + (i64)c * lda]);
+        __syncthreads();
+        const T inv = singular ? scalar_traits<T>::zero() : recip(u[j]);
+        T* colj = A + (i64)j * lda;
+        for (i64 i = r0 + t; i < r1; i += LU_THREADS)
+            if (!done[i]) colj[i] = colj[i] * inv;
+        __syncthreads();
+        double bv = -1.0;
+        long long bk = BIG, br = 0;
+        // a warp takes 32 consecutive rows of one column at a time; its lanes keep their row's multiplier in a register
+        // while the warp walks the columns
+        const int nc = n - j - 1;
+        const unsigned nchunk = (unsigned)((r1 - r0 + 31) >> 5);
+        const unsigned lane = t & 31, warp = t >> 5, nwarp = LU_THREADS >> 5;
+        // warps are spread over the chunks first, then over the columns of a chunk
+        const unsigned perChunk = nwarp > nchunk ? nwarp / nchunk : 1;
+        for (unsigned ch = warp / perChunk; ch < nchunk; ch += (nwarp + perChunk - 1) / perChunk) {
+            const i64 i = r0 + (i64)ch * 32 + lane;
+            const bool live = i < r1 && !done[i];
+            const T l = live ? colj[i] : scalar_traits<T>::zero();
+            if (!live) continue;
+            T* row = A + i;
+            int c = (int)(warp % perChunk);
+            const int pc = (int)perChunk;
+            if (PIVOT && c == 0 && nc > 0) {   // column j + 1 also yields the next pivot candidate of this row
+                T* p = row + (i64)(j + 1) * lda;
+                const T v = *p - l * u[j + 1];
+                *p = v;
+                const double a = abs1(v);
+                const long long key = (i < n) ? posTop[i] : i;
+                if (better2(a, key, bv, bk)) { bv = a; bk = key; br = i; }
+                c += pc;
+            }
+            // four columns in flight per lane: the loads are independent, the compiler cannot hoist them past the
+            // stores by itself
+            for (; c + 3 * pc < nc; c += 4 * pc) {
+                T* p0 = row + (i64)(j + 1 + c) * lda;
+                T* p1 = p0 + (i64)pc * lda;
+                T* p2 = p1 + (i64)pc * lda;
+                T* p3 = p2 + (i64)pc * lda;
+                const T a0 = *p0, a1 = *p1, a2 = *p2, a3 = *p3;
+                *p0 = a0 - l * u[j + 1 + c];
+                *p1 = a1 - l * u[j + 1 + c + pc];
+                *p2 = a2 - l * u[j + 1 + c + 2 * pc];
+                *p3 = a3 - l * u[j + 1 + c + 3 * pc];
+            }
+            for (; c < nc; c += pc) {
+                T* p = row + (i64)(j + 1 + c) * lda;
+                *p = *p - l * u[j + 1 + c];
+            }
+        }
+        if (PIVOT && j + 1 < n) {
+            block_reduce(bv, bk, br);
+            if (t == 0) { cand[blockIdx.x].val = bv; cand[blockIdx.x].key = bk; cand[blockIdx.x].row = br; }
+        }
+    }
+    if (!PIVOT) return;
+    // the rows whose position is not their physical index: pivot rows go to 0 .. n-1, displaced top rows to where
+    // their pivots came from.  Stage every source, meet, then write every destination.
+    grid_barrier(bar, nblk, epoch);
+    for (int slot = blockIdx.x; slot < 2 * n; slot += nblk) {
+        i64 src;
+        if (slot < n) { src = rowAt[slot]; if (src == slot) continue; }
+        else { src = slot - n; if (posTop[src] < n) continue; }
+        for (int c = t; c < n; c += LU_THREADS) stage[(i64)slot * n + c] = ldcg(&A[src + (i64)c * lda]);
+    }
+    grid_barrier(bar, nblk, epoch);
+    for (int slot = blockIdx.x; slot < 2 * n; slot += nblk) {
+        i64 dst;
+        if (slot < n) { if (rowAt[slot] == slot) continue; dst = slot; }
+        else { dst = posTop[slot - n]; if (dst < n) continue; }
+        for (int c = t; c < n; c += LU_THREADS) A[dst + (i64)c * lda] = stage[(i64)slot * n + c];
+    }
+}
+
 template <class T, bool PIVOT>
 void launch_panel(i64 M, int n, T* A, i64 lda, i64* ipiv, int* info, i64 col0, cudaStream_t s) {
     static int maxGrid = 0;
@@ -183,20 +376,40 @@ void launch_panel(i64 M, int n, T* A, i64 lda, i64* ipiv, int* info, i64 col0, c
         if (per < 1) throw std::runtime_error("getrf_panel: kernel does not fit an SM");
         maxGrid = sm_count();   // one CTA per SM: the slabs are bandwidth-, not occupancy-bound
     }
-    // at least 256 rows per CTA so that the per-column barriers are not the whole cost of a short panel
-    i64 grid = ceil_div(M, 256);
+    // as many CTAs as SMs once the panel has 64 rows per CTA: the slab of a CTA (rows x n) then stays in its L1, and the
+    // per-column work of a thread is a handful of elements (measured: 256 rows per CTA left 3/4 of the SMs idle at
+    // m = 8192 and made every column a 17 us walk through L2)
+    static const int minRows = [] { const char* e = std::getenv("ELB200_LU_PANEL_ROWS"); return e ? std::atoi(e) : 64; }();
+    i64 grid = ceil_div(M, minRows > 0 ? minRows : 64);
     if (grid > maxGrid) grid = maxGrid;
     if (grid < 1) grid = 1;
     i64 rows = ceil_div(ceil_div(M, grid), 32) * 32;
     if (rows > (i64(1) << 21)) throw std::logic_error("getrf_panel: panel taller than 2^21 rows per SM");
     grid = ceil_div(M, rows);
-    unsigned* bar = (unsigned*)scratch_alloc(256 + sizeof(Cand) * (size_t)grid, s);
-    Cand* cand = (Cand*)((char*)bar + 256);
-    ELB_CUDA(cudaMemsetAsync(bar, 0, 256, s));
-    void* args[] = {&M, &n, &A, &lda, &ipiv, &info, &col0, &bar, &cand, &rows};
-    ELB_CUDA(cudaLaunchCooperativeKernel((const void*)lu_panel_kernel<T, PIVOT>, dim3((unsigned)grid), dim3(LU_THREADS), args, 0, s));
+    static const int gen = [] { const char* e = std::getenv("ELB200_LU_PANEL_GEN"); return e ? std::atoi(e) : 2; }();
+    if (gen == 1) {   // first generation: physical interchanges, two barriers per column (kept for A/B runs)
+        unsigned* bar = (unsigned*)scratch_alloc(256 + sizeof(Cand) * (size_t)grid, s);
+        Cand* cand = (Cand*)((char*)bar + 256);
+        ELB_CUDA(cudaMemsetAsync(bar, 0, 256, s));
+        void* args[] = {&M, &n, &A, &lda, &ipiv, &info, &col0, &bar, &cand, &rows};
+        ELB_CUDA(cudaLaunchCooperativeKernel((const void*)lu_panel_kernel<T, PIVOT>, dim3((unsigned)grid), dim3(LU_THREADS), args, 0, s));
+        ++g_kernel_launches;
+        scratch_free(bar, s);
+        return;
+    }
+    const size_t candBytes = (sizeof(Cand2) * (size_t)grid + 255) / 256 * 256;
+    const size_t doneBytes = ((size_t)M + 255) / 256 * 256;
+    const size_t stageBytes = sizeof(T) * 2 * (size_t)n * (size_t)n;
+    char* ws = (char*)scratch_alloc(256 + candBytes + doneBytes + stageBytes, s);
+    unsigned* bar = (unsigned*)ws;
+    Cand2* cand = (Cand2*)(ws + 256);
+    unsigned char* done = (unsigned char*)(ws + 256 + candBytes);
+    T* stage = (T*)(ws + 256 + candBytes + doneBytes);
+    ELB_CUDA(cudaMemsetAsync(ws, 0, 256 + candBytes + doneBytes, s));
+    void* args[] = {&M, &n, &A, &lda, &ipiv, &info, &col0, &bar, &cand, &rows, &done, &stage};
+    ELB_CUDA(cudaLaunchCooperativeKernel((const void*)lu_panel_ip_kernel<T, PIVOT>, dim3((unsigned)grid), dim3(LU_THREADS), args, 0, s));
     ++g_kernel_launches;
-    scratch_free(bar, s);
+    scratch_free(ws, s);
 }
 
 // ---- interchange of the rows a panel's swap sequence touches -------------------------------------------------
