@@ -118,6 +118,7 @@ struct SlotInterchange {
         const D* all = buf;
         if (r > 1) {
             ELB_NCCL(ncclAllGather(buf, buf + perR, perR * sizeof(D), ncclInt8, (ncclComm_t)g.MCComm().nccl, s));
+            GetRedistStats().allGathers++;
             all = buf + perR;
         }
         elb200::unpack_rows_device<D>(S, slotIdx, srcSlot, dev::ptr(W.Buffer()), W.LDim(), nloc, W.ColAlign(), r, W.ColRank(),
@@ -128,6 +129,7 @@ struct SlotInterchange {
         all = buf;
         if (c > 1) {
             ELB_NCCL(ncclAllGather(buf, buf + perC, perC * sizeof(D), ncclInt8, (ncclComm_t)g.MRComm().nccl, s));
+            GetRedistStats().allGathers++;
             all = buf + perC;
         }
         elb200::unpack_cols_device<D>(S, slotIdx, srcSlot, dev::ptr(W.Buffer()), W.LDim(), mloc, W.RowAlign(), c, W.RowRank(),

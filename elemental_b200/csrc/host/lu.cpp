@@ -264,6 +264,7 @@ struct PanelSwapper {
             // every process of the column contributes its slots (fixed size: unowned slots travel as padding)
             const Comm& col = A.ColDist() == MC ? g.MCComm() : g.MRComm();
             ELB_NCCL(ncclAllGather(buf, buf + per, per * sizeof(D), ncclInt8, (ncclComm_t)col.nccl, s));
+            GetRedistStats().allGathers++;
             all = buf + per;
         }
         elb200::unpack_rows_device<D>(S, slotRow, srcSlot, dev::ptr(A.Buffer()), A.LDim(), nloc, A.ColAlign(), r, A.ColRank(),

@@ -22,6 +22,7 @@
 // in its own grid row / column, which makes every "filter" redistribution purely local.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <tuple>
 
@@ -108,7 +109,7 @@ void Redistribute(const AbstractDistMatrix<T>& A, AbstractDistMatrix<T>& B, bool
     T* Bbuf = B.Buffer();
 
     std::vector<elb200_lattice> packs, unpacks;
-    struct Wire { int peer; const void* sendPtr; void* recvPtr; size_t sendBytes, recvBytes; };
+    struct Wire { int peer; int v; const void* sendPtr; void* recvPtr; size_t sendBytes, recvBytes; };
     std::vector<Wire> wires;
 
     // ---- peer-memory path (Grid::P2PState): one channel per stream that issues redistributions ----
@@ -182,6 +183,7 @@ void Redistribute(const AbstractDistMatrix<T>& A, AbstractDistMatrix<T>& B, bool
         if (sm.empty && rm.empty) continue;
         Wire wv;
         wv.peer = g.WorldRankOf(qi, qj);
+        wv.v = v;
         wv.sendPtr = nullptr; wv.recvPtr = nullptr; wv.sendBytes = wv.recvBytes = 0;
         const bool sendP2P = ch >= 0 && !sm.empty && sizeof(T) * (size_t)sm.count() <= pp.regionBytes;
         const bool recvP2P = ch >= 0 && !rm.empty && sizeof(T) * (size_t)rm.count() <= pp.regionBytes;
@@ -231,6 +233,44 @@ void Redistribute(const AbstractDistMatrix<T>& A, AbstractDistMatrix<T>& B, bool
         LaunchLattices<T>(packs, false, nullptr, false);
         for (const Push& pu : pushes) ELB_CUDA(cudaMemcpyAsync(pu.dst, pu.src, pu.bytes, cudaMemcpyDefault, s));
     }
+    // AllGather pattern inside ONE communicator (the reference's RowAllGather.hpp:65-66, ColAllGather.hpp:72-73,
+    // PartialColAllGather.hpp:80-82): this process sends the same piece to, and receives a piece of the same size
+    // from, every other member of its grid row, grid column or the whole grid.  One ncclAllGather into staging in
+    // communicator-rank order replaces the grouped send/recv; the unpack reads the staging directly.  (Only pieces
+    // that do not ride the peer-memory path reach this point.)
+    std::vector<const T*> recvSrc(p, nullptr);
+    char* agStage = nullptr;
+    static const bool agOn = [] { const char* e = std::getenv("ELB200_NCCL_ALLGATHER"); return !(e && std::atoi(e) == 0); }();
+    if (agOn && !wires.empty() && wires[0].sendBytes > 0) {
+        const void* sp = wires[0].sendPtr;
+        const size_t bytes = wires[0].sendBytes;
+        bool same = true;
+        for (const Wire& wv : wires) same = same && wv.sendPtr == sp && wv.sendBytes == bytes && wv.recvBytes == bytes;
+        const Comm* comms[3] = {&g.MRComm(), &g.MCComm(), &g.VCComm()};
+        for (int ci = 0; same && ci < 3 && !agStage; ++ci) {
+            const Comm& cm = *comms[ci];
+            if (!cm.nccl || cm.size != (int)wires.size() + 1 || (int)cm.toWorld.size() != cm.size) continue;
+            std::vector<int> rankOf(wires.size(), -1);
+            bool match = cm.toWorld[cm.rank] == meW;
+            for (size_t q = 0; match && q < wires.size(); ++q) {
+                for (int t = 0; t < cm.size; ++t)
+                    if (cm.toWorld[t] == wires[q].peer) rankOf[q] = t;
+                match = rankOf[q] >= 0;
+            }
+            if (!match) continue;
+            agStage = (char*)elb200::scratch_alloc(bytes * (size_t)cm.size, s);
+            ELB_NCCL(ncclAllGather(sp, agStage, bytes, ncclInt8, (ncclComm_t)cm.nccl, s));
+            st.allGathers++;
+            st.messages += wires.size();
+            st.bytesSent += bytes * wires.size();
+            for (size_t q = 0; q < wires.size(); ++q) {
+                const char* slot = agStage + bytes * (size_t)rankOf[q];
+                if (recvOff[wires[q].v] >= 0) recvSrc[wires[q].v] = (const T*)slot;        // staged: unpack from here
+                else ELB_CUDA(cudaMemcpyAsync(wires[q].recvPtr, slot, bytes, cudaMemcpyDeviceToDevice, s));   // in place
+            }
+            wires.clear();
+        }
+    }
     if (!wires.empty()) {
         if (!g.WorldNccl()) RuntimeError("Multi-rank redistribution without an NCCL communicator");
         ELB_NCCL(ncclGroupStart());
@@ -276,7 +316,7 @@ void Redistribute(const AbstractDistMatrix<T>& A, AbstractDistMatrix<T>& B, bool
             if (recvOff[v] < 0) continue;
             const Msg& rm = recvMsg[v];
             elb200_lattice d;
-            d.src = recvBuf + recvOff[v]; d.dst = Bbuf;
+            d.src = recvSrc[v] ? recvSrc[v] : recvBuf + recvOff[v]; d.dst = Bbuf;
             d.nrows = rm.nrows; d.ncols = rm.ncols;
             d.s_off = 0; d.s_rs = 1; d.s_cs = rm.nrows;
             d.d_off = rm.d_off; d.d_rs = rm.d_rs; d.d_cs = rm.d_cs;
@@ -297,6 +337,7 @@ void Redistribute(const AbstractDistMatrix<T>& A, AbstractDistMatrix<T>& B, bool
         }
         elb200::p2p_flags(ops, s);
     }
+    if (agStage) elb200::scratch_free(agStage, s);
     elb200::scratch_free(packBuf, s);
     elb200::scratch_free(recvBuf, s);
 }
