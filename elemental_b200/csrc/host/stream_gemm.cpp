@@ -12,6 +12,8 @@
 // blocksize, band edges never split a k-panel), so the result is bit-identical to El::Gemm on device-resident
 // operands (tests/test_el_gpu.py::test_gemm_host_streamed_matches_device_gemm).
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "dev.hpp"
@@ -64,7 +66,17 @@ void GemmHost(Orientation oA, Orientation oB, T alpha, const Grid& g, const Host
     const Int bsize = Blocksize();
     // offsets that keep every local offset integral on both grid dimensions (and 16-element aligned for TMA)
     const Int granule = 16 * Lcm(g.Height(), g.Width());
-    const Int wantBands = 8, wantChunks = 8;
+    // ELB200_GEMMHOST_BANDS / _CHUNKS (read at every call) override the number of column bands of C / chunks of the
+    // summation index; results do not depend on them
+    auto envInt = [](const char* name, Int dflt) { const char* e = std::getenv(name); const Int v = e ? std::atoi(e) : 0; return v > 0 ? v : dflt; };
+    // Default number of bands: local bands of about 512 MB, between 2 and 8.  Every band repeats the whole panel loop
+    // (the A panels are gathered again) and pays its own first copy-in / last copy-out, so small local matrices want
+    // few bands; large ones want many, so that the copy of band j + 1 hides behind the product of band j.  Measured
+    // (profiles/r02_gemmhost_bands_n8.txt, n = 32768 on 2x4, local C 1.07 GB): 8 bands 492 ms, 4 bands 434 ms,
+    // 2 bands 413 ms; on one GPU (local C 8.6 GB) 8 bands hide all but 9 % of the copies.
+    const double localCBytes = double(sizeof(T)) * double((m + g.Height() - 1) / g.Height()) * double((n + g.Width() - 1) / g.Width());
+    const Int autoBands = (Int)std::min(8.0, std::max(2.0, std::ceil(localCBytes / double(size_t(512) << 20))));
+    const Int wantBands = envInt("ELB200_GEMMHOST_BANDS", autoBands), wantChunks = envInt("ELB200_GEMMHOST_CHUNKS", 8);
     const Int wb = std::max<Int>(granule, RoundUp((n + wantBands - 1) / wantBands, granule));
     const Int kc = std::max<Int>(Lcm(granule, bsize), RoundUp((k + wantChunks - 1) / wantChunks, Lcm(granule, bsize)));
     const Int nbands = std::max<Int>(1, (n + wb - 1) / wb);

@@ -61,12 +61,29 @@ def test_gemm_matches_reference_all_variants(El, dt):
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.complex128, np.float32])
-def test_gemm_host_streamed_matches_device_gemm(El, dt):
+def test_gemm_host_streamed_matches_device_gemm(El, dt, monkeypatch):
     """El.GemmHost (ElGemmDistHost_*: host-resident local matrices, C streamed through HBM in column bands, A in
     chunks of the summation index) against El.Gemm on device-resident copies of the same inputs.  alpha = -1:
-    bit-identical (same rank-nb updates in the same order); general alpha: the Gemm tolerance."""
-    m, n, k, nb = 210, 300, 200, 32     # 7 bands of 48 columns, 7 chunks of 32 summation indices
+    bit-identical (same rank-nb updates in the same order); general alpha: the Gemm tolerance.  The band count is
+    forced to 8 for the orientation sweep (the default picks 2 bands for matrices this small); the default and a
+    single band are run as well -- the result does not depend on the schedule."""
+    m, n, k, nb = 210, 300, 200, 32     # 8 wanted: 7 bands of 48 columns, 7 chunks of 32 summation indices
     g = El.Grid()
+    A, B, C0 = O.fill(0, m, k, 1, dtype=dt), O.fill(0, k, n, 2, dtype=dt), O.fill(0, m, n, 3, dtype=dt)
+    El.PushBlocksizeStack(nb)
+    dC = _dm(El, C0)
+    El.Gemm(0, 0, -1.0, _dm(El, A), _dm(El, B), 1.0, dC, El.GEMM_SUMMA_C)
+    want = dC.ToGlobal()
+    for bands in (None, "1", "3"):
+        if bands is None:
+            monkeypatch.delenv("ELB200_GEMMHOST_BANDS", raising=False)
+        else:
+            monkeypatch.setenv("ELB200_GEMMHOST_BANDS", bands)
+        hC = np.asfortranarray(C0.copy())
+        El.GemmHost(0, 0, -1.0, g, m, n, k, np.asfortranarray(A), np.asfortranarray(B), 1.0, hC, El.GEMM_SUMMA_C)
+        assert np.array_equal(hC, want), (dt, bands)
+    El.PopBlocksizeStack()
+    monkeypatch.setenv("ELB200_GEMMHOST_BANDS", "8")
     for oa in "NTC":
         for ob in "NTC":
             A = O.fill(0, *((m, k) if oa == "N" else (k, m)), 1, dtype=dt)
