@@ -241,8 +241,9 @@ def lu(A, nb=128):
     """El::LU(A) without pivoting (src/lapack_like/factor/LU.cpp:21-99), in place: unit-lower L and U packed."""
     assert A.flags.f_contiguous
     fn = getattr(lib(), "elref_lu_" + _SUF[A.dtype])
-    _chk3(fn(A.shape[0], A.shape[1], _p(A), A.shape[0], int(nb)))
-    return A
+    io = _InOut(A)
+    _chk3(fn(A.shape[0], A.shape[1], _p(io.buf), A.shape[0], int(nb)))
+    return io.done()
 
 
 def lu_piv(A, nb=128):

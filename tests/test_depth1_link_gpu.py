@@ -1,5 +1,5 @@
 """INTEGRATION.md depth 1, executed: the REFERENCE's own host code (El::Gemm SUMMA loops, El::Cholesky
-LowerVariant3Blocked + LocalTrrk recursion + unblocked diagonal block, El::HPDSolve, El::Trsm) running unmodified
+LowerVariant3Blocked + LocalTrrk recursion + unblocked diagonal block, El::HPDSolve, El::Trsm, El::LU) running unmodified
 against libelb200.so's Fortran BLAS symbols.
 
 oracle/_ref/libElRefDev.so is the same set of reference objects as libElRef.so, except that the two translation units
@@ -49,6 +49,9 @@ def run_all():
         out[f"hpd_{{tag}}"] = R.hpd_solve("L", "N", H, Bh.copy(order="F"), nb=nb)
         T = np.asfortranarray((O.fill(0, 200, 200, 7, dtype=dt) / 200 + 2 * np.eye(200)).astype(dt))
         out[f"trsm_{{tag}}"] = R.trsm("L", "L", "N", "N", 2.0, T, O.fill(0, 200, 50, 8, dtype=dt).copy(order="F"), nb=nb)
+        # El::LU without pivoting (LU.cpp:47-99): its LocalTrsm / LocalGemm leaves go to the GPU, lu::Unb stays on the host
+        D = np.asfortranarray((O.fill(0, 280, 280, 9, dtype=dt) + 280 * np.eye(280)).astype(dt))
+        out[f"lu_{{tag}}"] = R.lu(D.copy(order="F"), nb=nb)
     return out
 cpu = run_all()
 R.use_device_build(True)
