@@ -51,7 +51,10 @@ def run(grid, tag, variants):
 
 
 g1 = El.Grid(H) if world > 1 else El.Grid()
-run(g1, "p2p=on ", [(8, 8), (4, 8), (2, 8), (4, 4)])
+variants = [(8, 8), (4, 8), (2, 8), (4, 4)]
+if os.environ.get("BANDS_SWEEP"):   # e.g. BANDS_SWEEP="8x8,16x8,16x16"
+    variants = [tuple(int(x) for x in v.split("x")) for v in os.environ["BANDS_SWEEP"].split(",")]
+run(g1, "p2p=on ", variants)
 if world > 1:
     os.environ["ELB200_P2P"] = "0"
     g2 = El.Grid(H)
