@@ -18,6 +18,7 @@
 
 #include "dev.hpp"
 #include "elb200/lu.hpp"
+#include "elb200_plan.h"
 
 namespace El {
 
@@ -126,12 +127,11 @@ void DistPermutation::Compose() const {
     }
     pre_.resize(size_);
     img_.resize(size_);
-    std::iota(pre_.begin(), pre_.end(), i64(0));
-    for (Int j = 0; j < numSwaps_; ++j) {
-        if (o[j] < 0 || o[j] >= size_ || d[j] < 0 || d[j] >= size_) RuntimeError("Corrupt swap sequence");
-        std::swap(pre_[o[j]], pre_[d[j]]);   // the rows are swapped, so are their labels (Permutation.cpp:333-347)
-    }
-    for (Int i = 0; i < size_; ++i) img_[pre_[i]] = i;
+    // the bookkeeping itself is plain host code with a C entry point (include/elb200_plan.h), tested on the CPU
+    static_assert(sizeof(i64) == sizeof(int64_t), "swap lists are 64-bit");
+    if (elb200_perm_compose(size_, numSwaps_, (const int64_t*)o.data(), (const int64_t*)d.data(), (int64_t*)pre_.data(),
+                            (int64_t*)img_.data()) != 0)
+        RuntimeError("Corrupt swap sequence");
     if (vecSize_ < size_) {
         if (vec_) elb200::scratch_free(vec_, s);
         vec_ = (i64*)elb200::scratch_alloc(sizeof(i64) * 2 * (size_t)std::max<Int>(size_, 1), s);
@@ -150,14 +150,7 @@ const long long* DistPermutation::DeviceVector(bool inverse) const {
 }
 bool DistPermutation::Parity() const {
     Compose();
-    std::vector<char> seen(size_, 0);
-    Int cycles = 0;
-    for (Int i = 0; i < size_; ++i) {
-        if (seen[i]) continue;
-        ++cycles;
-        for (i64 j = i; !seen[j]; j = pre_[j]) seen[j] = 1;
-    }
-    return ((size_ - cycles) & 1) != 0;
+    return elb200_perm_parity(size_, (const int64_t*)pre_.data()) != 0;
 }
 Int DistPermutation::Image(Int origin) const {
     if (origin < 0 || origin >= size_) LogicError("Index out of range");

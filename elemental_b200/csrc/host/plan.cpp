@@ -203,3 +203,33 @@ int elb200_gemm_default_algorithm(int64_t m, int64_t n, int64_t k) {
 }
 
 }  // extern "C"
+
+extern "C" {
+int elb200_perm_compose(int64_t size, int64_t nswaps, const int64_t* origins, const int64_t* dests, int64_t* pre,
+                        int64_t* img) {
+    if (size < 0 || nswaps < 0) return 1;
+    for (int64_t i = 0; i < size; ++i) pre[i] = i;
+    for (int64_t j = 0; j < nswaps; ++j) {
+        const int64_t o = origins[j], d = dests[j];
+        if (o < 0 || o >= size || d < 0 || d >= size) return 1;
+        const int64_t t = pre[o];   // the rows trade places, so do their labels
+        pre[o] = pre[d];
+        pre[d] = t;
+    }
+    if (img)
+        for (int64_t i = 0; i < size; ++i) img[pre[i]] = i;
+    return 0;
+}
+int elb200_perm_parity(int64_t size, const int64_t* pre) {
+    // a permutation with c cycles is a product of size - c transpositions
+    std::vector<char> seen((size_t)(size > 0 ? size : 0), 0);
+    int64_t cycles = 0;
+    for (int64_t i = 0; i < size; ++i) {
+        if (seen[(size_t)i]) continue;
+        ++cycles;
+        for (int64_t j = i; !seen[(size_t)j]; j = pre[j]) seen[(size_t)j] = 1;
+    }
+    return (int)((size - cycles) & 1);
+}
+}
+

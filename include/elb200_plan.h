@@ -58,6 +58,14 @@ int elb200_dist_stride(int dist, int r, int c);
 int elb200_dist_rank(int dist, int r, int c, int row, int col);
 int elb200_gemm_default_algorithm(int64_t m, int64_t n, int64_t k);
 
+/* Permutation bookkeeping of DistPermutation (src/lapack_like/perm/Permutation.cpp:333-347 MakeArbitrary, :300-322
+ * Image / Preimage, Parity): compose `nswaps` swaps (origins[j] <-> dests[j], applied in order) of `size` indices into
+ * the explicit vectors: row i of P A is row preimages[i] of A, images[preimages[i]] = i.  Returns 0, or 1 when an
+ * index is out of range.  elb200_perm_parity: 1 when the permutation is odd, 0 when even. */
+int elb200_perm_compose(int64_t size, int64_t nswaps, const int64_t* origins, const int64_t* dests, int64_t* preimages,
+                        int64_t* images);
+int elb200_perm_parity(int64_t size, const int64_t* preimages);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,3 +141,34 @@ def test_contract_plans(r, c):
                 ca = 1 % (r if u == MC else (c if u == MR else 1))
                 ra = 1 % (c if v == MR else (r if v == MC else 1))
                 _run_contract(r, c, Layout(u, v, ca, ra), Layout(bu, bv, (1 % r) if bu == MC else (1 % c), 0), h, w)
+
+
+def test_permutation_bookkeeping_matches_sequential_swaps():
+    """elb200_perm_compose / elb200_perm_parity (the host logic of El::DistPermutation, Permutation.cpp:333-347):
+    swaps applied in order to the identity give the preimage vector; images invert it; parity = sign of the
+    permutation (determinant of the permutation matrix)."""
+    import ctypes as C
+    from elemental_b200._lib import lib
+    L = lib()
+    rng = np.random.default_rng(77)
+    for trial in range(40):
+        n = int(rng.integers(1, 40))
+        k = int(rng.integers(0, 60))
+        o = rng.integers(0, n, k).astype(np.int64)
+        d = rng.integers(0, n, k).astype(np.int64)
+        pre = np.zeros(n, dtype=np.int64)
+        img = np.zeros(n, dtype=np.int64)
+        P64 = C.POINTER(C.c_int64)
+        rc = L.elb200_perm_compose(C.c_int64(n), C.c_int64(k), o.ctypes.data_as(P64), d.ctypes.data_as(P64),
+                                   pre.ctypes.data_as(P64), img.ctypes.data_as(P64))
+        assert rc == 0
+        want = np.arange(n)
+        for a, b in zip(o, d):
+            want[[a, b]] = want[[b, a]]
+        assert np.array_equal(pre, want)
+        assert np.array_equal(img[pre], np.arange(n))
+        Pm = np.eye(n)[pre]                       # row i of P A is row pre[i] of A
+        assert L.elb200_perm_parity(C.c_int64(n), pre.ctypes.data_as(P64)) == (0 if round(np.linalg.det(Pm)) == 1 else 1)
+    bad = np.array([5], dtype=np.int64)
+    assert L.elb200_perm_compose(C.c_int64(3), C.c_int64(1), bad.ctypes.data_as(P64), bad.ctypes.data_as(P64),
+                                 pre.ctypes.data_as(P64), img.ctypes.data_as(P64)) == 1
