@@ -873,7 +873,13 @@ template <typename F>
 void TrsmLeft(UpperOrLower uplo, Orientation o, UnitOrNonUnit diag, const AbstractDistMatrix<F>& L,
               AbstractDistMatrix<F>& X, int* singularFlag, bool medium) {
     const Grid& g = X.Grid();
-    const Int mTri = L.Height(), bsize = Blocksize(), nrhs = X.Width();
+    // The block loop runs on ELB200_TRSM_BLOCK_FACTOR (default 4) x Blocksize() rows at a time: the solve is a chain of
+    // dependent steps (three redistributions, a small solve and a rank-nb product each), latency-bound long before it
+    // is flop-bound -- at Blocksize() = 128 and 1024 right-hand sides on 2x4 GPUs a step costs ~0.4 ms for 0.1 ms of
+    // arithmetic.  Four blocks per step pay that chain a quarter as often; the diagonal block grows to 512 x 512,
+    // which the local kernel solves in its own 32-wide sweeps.  The result is the same up to the order of the sums.
+    const Int factor = [] { const char* e = std::getenv("ELB200_TRSM_BLOCK_FACTOR"); const int v = e ? std::atoi(e) : 4; return v >= 1 ? v : 1; }();
+    const Int mTri = L.Height(), bsize = Blocksize() * factor, nrhs = X.Width();
     const bool effLower = (uplo == LOWER) == (o == NORMAL);
     const bool forward = effLower;
     const Int nblk = (mTri + bsize - 1) / bsize;
